@@ -1,0 +1,126 @@
+// Shared device/host helpers for libclimatrix_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/climatrix_b200.h"
+
+namespace cmx {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---- host-side bookkeeping (thread-local) ---------------------------------
+void note_launch();                 // ++launch counter
+int cuda_fail(cudaError_t e);       // records text, returns CMX_ERR_CUDA
+int check_launch();                 // cudaGetLastError() -> CMX_OK / CMX_ERR_CUDA
+int sm_count();                     // SMs of the current device (cached)
+
+#define CMX_CUDA(call)                                   \
+    do {                                                 \
+        cudaError_t _e = (call);                         \
+        if (_e != cudaSuccess) return ::cmx::cuda_fail(_e); \
+    } while (0)
+
+// ---- neighbour-search core, shared by cmx_knn / cmx_idw_* / cmx_ok_mw_* ----
+struct KnnJob {
+    // samples: coordinate a pairs with the targets' row axis, b with the column axis
+    const double* s_a;
+    const double* s_b;
+    long long n;
+    // targets
+    const double* t_a;
+    const double* t_b;
+    long long n_a, n_b;
+    int grid;  // 1: dense grid (n_a rows x n_b cols), 0: explicit points (n_a == n_b == M)
+    int k;
+    // raw neighbour table (any may be null)
+    int* idx_out;      // [M][k]
+    double* dist_out;  // [M][k]  sqrt(d2)
+    double* d2_out;    // [M][k]  exact squared distance
+    // fused IDW epilogue (idw.py:163-180); mode 0 = off
+    int idw_mode;      // 1: single slice -> out[M];  2: write normalised weights -> w_out[M][k]
+    int value_is_f32;  // dtype of vals/out
+    const void* vals;  // [N] (mode 1)
+    void* out;         // [M] (mode 1)
+    double* w_out;     // [M][k] (mode 2)
+    int k_min;
+    double power;
+    // scratch
+    void* workspace;
+    size_t workspace_bytes;
+};
+size_t knn_workspace_bytes(int k);
+int run_knn(const KnnJob& job, cudaStream_t stream);
+
+// ---- device helpers -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on `bar` (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+
+// IDW weight of one neighbour before normalisation: 1 / max(d, 1e-10)^power  (idw.py:163-164)
+__device__ __forceinline__ double idw_weight_from_dist(double dist, double power) {
+    const double d = fmax(dist, 1e-10);
+    if (power == 2.0) return 1.0 / (d * d);  // numpy evaluates x**2.0 as x*x
+    return 1.0 / pow(d, power);
+}
+__device__ __forceinline__ double idw_raw_weight(double d2, double power) {
+    return idw_weight_from_dist(sqrt(d2), power);
+}
+
+template <typename V>
+__device__ __forceinline__ V quiet_nan();
+template <>
+__device__ __forceinline__ float quiet_nan<float>() { return __int_as_float(0x7fc00000); }
+template <>
+__device__ __forceinline__ double quiet_nan<double>() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+}  // namespace cmx

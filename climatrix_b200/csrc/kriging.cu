@@ -1,0 +1,323 @@
+// K4: batched moving-window ordinary kriging -- one warp per target.
+//
+// Replaces pykrige OrdinaryKriging.execute(..., backend="loop", n_closest_points=k)
+// (_exec_loop_moving_window), reached from the reference call site
+// src/climatrix/reconstruct/kriging.py:236-241; algorithm restated in SURVEY.md
+// Appendix A.2 step 5.  Per target, with its k nearest samples s_1..s_k (from K1, run
+// in the kriging frame) and distances bd_j:
+//
+//     [ G   1 ] [x ]   [ b ]      G_ij = -gamma(|s_i - s_j|), G_ii = 0
+//     [ 1^T 0 ] [mu] = [ 1 ]      b_j  = -gamma(bd_j)   (0 where bd_j <= 1e-10)
+//     z = sum_j x_j Z_j ,  sigma^2 = -(x.b + mu)
+//
+// The bordered system is solved by block elimination on the k x k core with two
+// right-hand sides (G y = b, G u = 1, mu = (1.y - 1)/(1.u), x = y - mu u), so that the
+// k rows map 1:1 onto the lanes of a warp.  G is symmetric indefinite (zero diagonal):
+// Gauss-Jordan elimination with partial (row) pivoting in float64, the matrix held
+// column-major in shared memory (conflict-free lane-per-row updates, pivot row read by
+// broadcast).  Tensor cores are not applicable: these are M independent tiny solves.
+// FP64-pipe + shared-memory bound; algorithmic FLOP per target
+//   ~ k^2 (5 + gamma) assemble + k^3 Gauss-Jordan + 6k.
+#include "common.cuh"
+
+namespace cmx {
+namespace {
+
+constexpr double OK_EPS = 1.0e-10;  // pykrige ok.py: eps
+
+struct OkArgs {
+    const double* s_x;
+    const double* s_y;
+    const void* z;
+    int z_is_f32;
+    const int* idx;     // [M][k]
+    const double* d2;   // [M][k] exact squared distances (kriging frame)
+    long long M;
+    int k;
+    int model;
+    double p0, p1, p2;
+    int exact_values;
+    double out_scale, out_shift;
+    void* out;
+    void* sigmasq;
+    int* n_singular;
+};
+
+// pykrige/variogram_models.py
+__device__ __forceinline__ double gamma_of(int model, double p0, double p1, double p2, double d) {
+    switch (model) {
+        case CMX_VARIOGRAM_LINEAR:  // slope * d + nugget
+            return p0 * d + p1;
+        case CMX_VARIOGRAM_POWER:  // scale * d^exponent + nugget
+            return p0 * pow(d, p1) + p2;
+        case CMX_VARIOGRAM_GAUSSIAN: {  // psill (1 - exp(-d^2 / (range 4/7)^2)) + nugget
+            const double r = p1 * 4.0 / 7.0;
+            return p0 * (1.0 - exp(-(d * d) / (r * r))) + p2;
+        }
+        case CMX_VARIOGRAM_SPHERICAL:  // psill (3d/(2r) - d^3/(2r^3)) + nugget, d <= r; psill + nugget beyond
+            if (d <= p1) return p0 * ((3.0 * d) / (2.0 * p1) - (d * d * d) / (2.0 * p1 * p1 * p1)) + p2;
+            return p0 + p2;
+        default:  // exponential: psill (1 - exp(-d / (range/3))) + nugget
+            return p0 * (1.0 - exp(-d / (p1 / 3.0))) + p2;
+    }
+}
+
+// E = ceil(k / 32) rows per lane; ld = 32 * E (column stride, in doubles)
+template <int E, typename V>
+__global__ void __launch_bounds__(256) ok_solve_kernel(const OkArgs a, int warps_per_cta) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int LD = 32 * E;
+    const int k = a.k;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    // per warp: matrix (k+2) columns x LD rows, then neighbour coordinates, then pivot rows
+    const size_t per_warp = (size_t)(k + 2) * LD * sizeof(double) + 2 * LD * sizeof(double) + LD * sizeof(int);
+    unsigned char* base = smem_raw + (size_t)warp * per_warp;
+    double* mat = reinterpret_cast<double*>(base);
+    double* cx = mat + (size_t)(k + 2) * LD;
+    double* cy = cx + LD;
+    int* piv = reinterpret_cast<int*>(cy + LD);
+    double* colB = mat + (size_t)k * LD;        // right-hand side b
+    double* colO = mat + (size_t)(k + 1) * LD;  // right-hand side of ones
+
+    const long long total_warps = (long long)gridDim.x * warps_per_cta;
+    for (long long m = (long long)blockIdx.x * warps_per_cta + warp; m < a.M; m += total_warps) {
+        // ---- gather the window ----
+        double mx[E], my[E], mz[E], borig[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int r = e * 32 + lane;
+            mx[e] = my[e] = mz[e] = borig[e] = 0.0;
+            if (r < k) {
+                const int id = a.idx[m * k + r];
+                mx[e] = a.s_x[id];
+                my[e] = a.s_y[id];
+                mz[e] = a.z_is_f32 ? (double)static_cast<const float*>(a.z)[id] : static_cast<const double*>(a.z)[id];
+                const double bd = sqrt(a.d2[m * k + r]);
+                double b = -gamma_of(a.model, a.p0, a.p1, a.p2, bd);
+                if (a.exact_values && fabs(bd) <= OK_EPS) b = 0.0;
+                borig[e] = b;
+                cx[r] = mx[e];
+                cy[r] = my[e];
+                colB[r] = b;
+                colO[r] = 1.0;
+            }
+        }
+        __syncwarp();
+        // ---- assemble G (column j = neighbour j; lanes own rows) ----
+        for (int j = 0; j < k; ++j) {
+            const double xj = cx[j], yj = cy[j];
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int r = e * 32 + lane;
+                if (r < k) {
+                    const double dx = __dsub_rn(mx[e], xj), dy = __dsub_rn(my[e], yj);
+                    const double d = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                    mat[(size_t)j * LD + r] = (r == j) ? 0.0 : -gamma_of(a.model, a.p0, a.p1, a.p2, d);
+                }
+            }
+        }
+        __syncwarp();
+        // ---- Gauss-Jordan with partial pivoting ----
+        unsigned done = 0;  // bit e: my row e*32+lane has been a pivot
+        bool singular = false;
+        for (int c = 0; c < k; ++c) {
+            double best = -1.0;
+            int brow = 0x7fffffff;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int r = e * 32 + lane;
+                if (r < k && !((done >> e) & 1u)) {
+                    const double v = fabs(mat[(size_t)c * LD + r]);
+                    if (v > best) {  // first maximum wins inside a lane (rows ascend with e)
+                        best = v;
+                        brow = r;
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(kFull, best, o);
+                const int orow = __shfl_xor_sync(kFull, brow, o);
+                if (ob > best || (ob == best && orow < brow)) {
+                    best = ob;
+                    brow = orow;
+                }
+            }
+            if (!(best > 0.0)) {  // zero (or NaN) column: singular window
+                singular = true;
+                break;
+            }
+            const int p = brow;
+            if ((p & 31) == lane) done |= 1u << (p >> 5);
+            if (lane == 0) piv[c] = p;
+            const double pinv = 1.0 / mat[(size_t)c * LD + p];
+            double f[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int r = e * 32 + lane;
+                f[e] = (r < k && r != p) ? mat[(size_t)c * LD + r] * pinv : 0.0;
+            }
+            __syncwarp();
+            for (int cc = c + 1; cc < k + 2; ++cc) {
+                const double pv = mat[(size_t)cc * LD + p];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int r = e * 32 + lane;
+                    if (r < k && r != p) mat[(size_t)cc * LD + r] = fma(-f[e], pv, mat[(size_t)cc * LD + r]);
+                }
+            }
+            __syncwarp();
+        }
+        // ---- back out x, mu; estimate and variance ----
+        double res = quiet_nan<double>(), var = quiet_nan<double>();
+        if (!singular) {
+            double y[E], u[E];
+            double sy = 0.0, su = 0.0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int c = e * 32 + lane;
+                y[e] = u[e] = 0.0;
+                if (c < k) {
+                    const int p = piv[c];
+                    const double dinv = 1.0 / mat[(size_t)c * LD + p];
+                    y[e] = colB[p] * dinv;
+                    u[e] = colO[p] * dinv;
+                    sy += y[e];
+                    su += u[e];
+                }
+            }
+            sy = warp_sum(sy);
+            su = warp_sum(su);
+            const double mu = (sy - 1.0) / su;
+            double zz = 0.0, xb = 0.0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const double x = y[e] - mu * u[e];
+                zz = fma(x, mz[e], zz);
+                xb = fma(x, borig[e], xb);
+            }
+            zz = warp_sum(zz);
+            xb = warp_sum(xb);
+            res = zz * a.out_scale + a.out_shift;
+            var = -(xb + mu);
+            if (!isfinite(mu)) singular = true;
+        }
+        if (lane == 0) {
+            if (singular) {
+                res = quiet_nan<double>();
+                var = quiet_nan<double>();
+                if (a.n_singular) atomicAdd(a.n_singular, 1);
+            }
+            static_cast<V*>(a.out)[m] = (V)res;
+            if (a.sigmasq) static_cast<V*>(a.sigmasq)[m] = (V)var;
+        }
+        __syncwarp();
+    }
+}
+
+template <int E, typename V>
+int launch_ok(const OkArgs& a, cudaStream_t stream) {
+    const int k = a.k;
+    const size_t per_warp = (size_t)(k + 2) * 32 * E * sizeof(double) + 2 * 32 * E * sizeof(double) + 32 * E * sizeof(int);
+    int warps = (int)((200 * 1024) / per_warp);
+    warps = warps > 8 ? 8 : (warps < 1 ? 1 : warps);
+    const size_t smem = per_warp * warps;
+    CMX_CUDA(cudaFuncSetAttribute(ok_solve_kernel<E, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long ctas = (a.M + warps - 1) / warps;
+    const long long cap = (long long)sm_count() * 8;
+    if (ctas > cap) ctas = cap;
+    ok_solve_kernel<E, V><<<(unsigned)ctas, warps * 32, smem, stream>>>(a, warps);
+    note_launch();
+    return check_launch();
+}
+
+template <typename V>
+int ok_entry(const double* s_x, const double* s_y, const V* z, int64_t n, const double* t_x, int64_t n_x,
+             const double* t_y, int64_t n_y, int grid, int metric, int k, int model, const double* params,
+             int exact_values, double out_scale, double out_shift, V* out, V* sigmasq, int32_t* n_singular,
+             void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!s_x || !s_y || !z || !t_x || !t_y || !params || !out) return CMX_ERR_BAD_ARG;
+    if (model < CMX_VARIOGRAM_LINEAR || model > CMX_VARIOGRAM_EXPONENTIAL) return CMX_ERR_UNSUPPORTED;
+    if (metric != CMX_METRIC_EUCLIDEAN) return CMX_ERR_UNSUPPORTED;  // geographic: chord kNN not built yet
+    if (k < 1) return CMX_ERR_BAD_ARG;
+    if (k > CMX_MAX_K) return CMX_ERR_K_TOO_LARGE;
+    if (n_x < 0 || n_y < 0) return CMX_ERR_BAD_ARG;
+    const long long M = grid ? (long long)n_x * n_y : (long long)n_x;
+    const size_t knn_ws = knn_workspace_bytes(k);
+    if (!workspace || workspace_bytes < cmx_ok_workspace_bytes(k, M)) return CMX_ERR_WORKSPACE;
+    unsigned char* extra = static_cast<unsigned char*>(workspace) + knn_ws;
+    extra = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(extra) + 255) & ~uintptr_t(255));
+    double* d2_tab = reinterpret_cast<double*>(extra);
+    int* idx_tab = reinterpret_cast<int*>(extra + (size_t)M * k * sizeof(double));
+
+    // neighbours in the kriging frame: rows of a dense target grid run along y (lat), columns along x (lon)
+    KnnJob job{};
+    job.s_a = s_y;
+    job.s_b = s_x;
+    job.n = n;
+    job.t_a = t_y;
+    job.t_b = t_x;
+    job.n_a = grid ? n_y : n_x;
+    job.n_b = n_x;
+    job.grid = grid;
+    job.k = k;
+    job.idx_out = idx_tab;
+    job.d2_out = d2_tab;
+    job.workspace = workspace;
+    job.workspace_bytes = knn_ws;
+    int rc = run_knn(job, stream);
+    if (rc != CMX_OK) return rc;
+    if (M == 0) return CMX_OK;
+
+    OkArgs a;
+    a.s_x = s_x;
+    a.s_y = s_y;
+    a.z = z;
+    a.z_is_f32 = sizeof(V) == 4;
+    a.idx = idx_tab;
+    a.d2 = d2_tab;
+    a.M = M;
+    a.k = k;
+    a.model = model;
+    a.p0 = params[0];
+    a.p1 = params[1];
+    a.p2 = params[2];
+    a.exact_values = exact_values;
+    a.out_scale = out_scale;
+    a.out_shift = out_shift;
+    a.out = out;
+    a.sigmasq = sigmasq;
+    a.n_singular = n_singular;
+    if (k <= 32) return launch_ok<1, V>(a, stream);
+    if (k <= 64) return launch_ok<2, V>(a, stream);
+    return launch_ok<4, V>(a, stream);
+}
+
+}  // namespace
+}  // namespace cmx
+
+extern "C" {
+
+size_t cmx_ok_workspace_bytes(int k, int64_t n_targets) {
+    if (k < 1 || k > CMX_MAX_K || n_targets < 0) return 0;
+    return cmx::knn_workspace_bytes(k) + (size_t)n_targets * (size_t)k * (sizeof(double) + sizeof(int)) + 1024;
+}
+
+int cmx_ok_mw_f64(const double* s_x, const double* s_y, const double* z, int64_t n, const double* t_x, int64_t n_x,
+                  const double* t_y, int64_t n_y, int grid, int metric, int k, int model, const double params[3],
+                  int exact_values, double out_scale, double out_shift, double* out, double* sigmasq,
+                  int32_t* n_singular, void* ws, size_t ws_bytes, void* stream) {
+    return cmx::ok_entry<double>(s_x, s_y, z, n, t_x, n_x, t_y, n_y, grid, metric, k, model, params, exact_values,
+                                 out_scale, out_shift, out, sigmasq, n_singular, ws, ws_bytes, stream);
+}
+int cmx_ok_mw_f32(const double* s_x, const double* s_y, const float* z, int64_t n, const double* t_x, int64_t n_x,
+                  const double* t_y, int64_t n_y, int grid, int metric, int k, int model, const double params[3],
+                  int exact_values, double out_scale, double out_shift, float* out, float* sigmasq,
+                  int32_t* n_singular, void* ws, size_t ws_bytes, void* stream) {
+    return cmx::ok_entry<float>(s_x, s_y, z, n, t_x, n_x, t_y, n_y, grid, metric, k, model, params, exact_values,
+                                out_scale, out_shift, out, sigmasq, n_singular, ws, ws_bytes, stream);
+}
+
+}  // extern "C"

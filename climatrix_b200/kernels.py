@@ -1,0 +1,307 @@
+"""Array-level API over the C ABI: torch CUDA tensors in, torch CUDA tensors out.
+
+PyTorch is used only for device memory, streams and (elsewhere)
+``torch.distributed``; every computation happens inside
+``libclimatrix_b200.so`` (``include/climatrix_b200.h``).  There is no CPU path:
+tensors must live on a CUDA device and the library must have been built.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+
+__all__ = [
+    "Targets",
+    "knn",
+    "idw",
+    "idw_apply",
+    "empirical_variogram",
+    "ok_moving_window",
+    "launch_count",
+    "reset_launch_count",
+]
+
+
+@dataclass
+class Targets:
+    """Target points: a dense (lat x lon) grid given by its axes, or explicit points.
+
+    Mirrors ``DenseDomain`` / ``SparseDomain.get_all_spatial_points``
+    (reference dataset/domain.py:917-922 / :738) without materialising the
+    (M, 2) array for grids: the kernels generate grid coordinates from the axes.
+    """
+
+    lat: torch.Tensor  # float64, cuda; grid: (n_lat,), points: (M,)
+    lon: torch.Tensor  # float64, cuda; grid: (n_lon,), points: (M,)
+    grid: bool
+
+    @property
+    def count(self) -> int:
+        return self.lat.numel() * self.lon.numel() if self.grid else self.lat.numel()
+
+    @property
+    def shape(self) -> tuple:
+        return (self.lat.numel(), self.lon.numel()) if self.grid else (self.lat.numel(),)
+
+    @staticmethod
+    def make(lat, lon, grid: bool, device) -> "Targets":
+        lat = _as_f64(lat, device)
+        lon = _as_f64(lon, device)
+        if lat.dim() != 1 or lon.dim() != 1:
+            raise ValueError("target latitude/longitude must be one-dimensional")
+        if not grid and lat.numel() != lon.numel():
+            raise ValueError("For sparse domain, lat and lon must have the same length")
+        return Targets(lat, lon, grid)
+
+    def row_band(self, r0: int, r1: int) -> "Targets":
+        """Rows [r0, r1) of a grid (or points [r0, r1)): the unit of multi-GPU sharding."""
+        if self.grid:
+            return Targets(self.lat[r0:r1].contiguous(), self.lon, True)
+        return Targets(self.lat[r0:r1].contiguous(), self.lon[r0:r1].contiguous(), False)
+
+
+def _require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "climatrix_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback."
+        )
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"climatrix_b200 runs on CUDA devices only, got {device}")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+def _as_f64(x, device) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.float64).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).to(device, non_blocking=True)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_workspaces: dict = {}
+
+
+def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    """Grow-only scratch per (device, stream): kernels on one stream run in order."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def launch_count() -> int:
+    return int(_lib.load().cmx_launch_count())
+
+
+def reset_launch_count() -> None:
+    _lib.load().cmx_reset_launch_count()
+
+
+def _check_samples(s_lat, s_lon):
+    if s_lat.dim() != 1 or s_lat.shape != s_lon.shape:
+        raise ValueError(
+            "Expected a 2D NumPy array with shape (N, 2) from get_all_spatial_points(), "
+            f"but got coordinates with shapes {tuple(s_lat.shape)} and {tuple(s_lon.shape)}."
+        )
+
+
+def knn(s_lat, s_lon, targets: Targets, k: int, *, return_distance: bool = True):
+    """k nearest samples of every target: ``(dist (M,k) f64 | None, idx (M,k) int32)``.
+
+    Replaces ``cKDTree(points).query(targets, k, workers=-1)`` (idw.py:155-158):
+    Euclidean in the flat (lat, lon) plane, rows ascending by (distance, index).
+    """
+    lib = _lib.load()
+    dev = _require_cuda(targets.lat.device)
+    s_lat, s_lon = _as_f64(s_lat, dev), _as_f64(s_lon, dev)
+    _check_samples(s_lat, s_lon)
+    k = int(k)
+    m = targets.count
+    with torch.cuda.device(dev):
+        idx = torch.empty((m, k), dtype=torch.int32, device=dev)
+        dist = torch.empty((m, k), dtype=torch.float64, device=dev) if return_distance else None
+        ws = _workspace(lib.cmx_knn_workspace_bytes(max(1, min(k, _lib.MAX_K))), dev)
+        rc = lib.cmx_knn(_ptr(s_lat), _ptr(s_lon), s_lat.numel(), _ptr(targets.lat), targets.lat.numel(),
+                         _ptr(targets.lon), targets.lon.numel(), int(targets.grid), k, _ptr(idx), _ptr(dist),
+                         _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "cmx_knn")
+    return dist, idx
+
+
+def _values_layout(values: torch.Tensor, n: int, layout: str | None):
+    """Returns (tensor, n_batch, layout_code).  Accepts (N,), (T,N) or (N,T)."""
+    if values.dim() == 1:
+        if values.numel() != n:
+            raise ValueError(f"values has {values.numel()} entries for {n} samples")
+        return values.contiguous(), 1, _lib.LAYOUT_BATCH_MAJOR
+    if values.dim() != 2:
+        raise ValueError("values must be (N,), (T, N) or (N, T)")
+    if layout is None:
+        layout = "sample_major" if (values.shape[0] == n and values.shape[1] != n) else "batch_major"
+    if layout == "batch_major":
+        if values.shape[1] != n:
+            raise ValueError(f"values (T, N) has {values.shape[1]} samples, expected {n}")
+        return values.contiguous(), values.shape[0], _lib.LAYOUT_BATCH_MAJOR
+    if layout == "sample_major":
+        if values.shape[0] != n:
+            raise ValueError(f"values (N, T) has {values.shape[0]} samples, expected {n}")
+        return values.contiguous(), values.shape[1], _lib.LAYOUT_SAMPLE_MAJOR
+    raise ValueError(f"unknown layout {layout!r}")
+
+
+def idw(s_lat, s_lon, values, targets: Targets, *, k: int = 5, power: float = 2.0, k_min: int = 2,
+        dtype: torch.dtype = torch.float64, layout: str | None = None, return_neighbours: bool = False,
+        out: torch.Tensor | None = None):
+    """Inverse-distance weighting on the device (reference idw.py:155-180).
+
+    ``values``: (N,) one slice, or a time/level batch as (T, N) ("batch_major") or
+    (N, T) ("sample_major", the fast layout).  Returns (M,) or (T, M) in ``dtype``;
+    with ``return_neighbours`` also ``(dist, idx)``.
+    """
+    lib = _lib.load()
+    dev = _require_cuda(targets.lat.device)
+    if dtype not in (torch.float64, torch.float32):
+        raise TypeError("dtype must be torch.float64 or torch.float32")
+    s_lat, s_lon = _as_f64(s_lat, dev), _as_f64(s_lon, dev)
+    _check_samples(s_lat, s_lon)
+    n = s_lat.numel()
+    if not isinstance(values, torch.Tensor):
+        values = torch.as_tensor(np.ascontiguousarray(values))
+    values = values.to(device=dev, dtype=dtype)
+    values, n_batch, layout_code = _values_layout(values, n, layout)
+    k, k_min = int(k), int(k_min)
+    m = targets.count
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty((n_batch, m) if n_batch > 1 or values.dim() == 2 else (m,), dtype=dtype, device=dev)
+        elif out.dtype != dtype or out.numel() != n_batch * m or not out.is_contiguous():
+            raise ValueError("out has the wrong dtype, size or is not contiguous")
+        idx = dist = None
+        if return_neighbours:
+            idx = torch.empty((m, k), dtype=torch.int32, device=dev)
+            dist = torch.empty((m, k), dtype=torch.float64, device=dev)
+        kk = max(1, min(k, _lib.MAX_K))
+        ws = _workspace(lib.cmx_knn_workspace_bytes(kk) + lib.cmx_idw_workspace_bytes(kk, m, n_batch), dev)
+        fn = lib.cmx_idw_f64 if dtype == torch.float64 else lib.cmx_idw_f32
+        rc = fn(_ptr(s_lat), _ptr(s_lon), n, _ptr(values), n_batch, layout_code, _ptr(targets.lat),
+                targets.lat.numel(), _ptr(targets.lon), targets.lon.numel(), int(targets.grid), k, k_min,
+                float(power), _ptr(out), _ptr(idx), _ptr(dist), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "cmx_idw")
+    if return_neighbours:
+        return out, dist, idx
+    return out
+
+
+def idw_apply(idx: torch.Tensor, dist: torch.Tensor, values, *, k: int | None = None, power: float = 2.0,
+              k_min: int = 2, dtype: torch.dtype = torch.float64, layout: str | None = None,
+              n_samples: int | None = None):
+    """Re-weight a stored neighbour table (hyper-parameter search inner loop:
+    reference optim/bayesian.py:399-405 calls reconstruct() once per trial; the
+    neighbour query only depends on max k, so it is hoisted)."""
+    lib = _lib.load()
+    dev = _require_cuda(idx.device)
+    m, k_table = idx.shape
+    k = k_table if k is None else int(k)
+    if not isinstance(values, torch.Tensor):
+        values = torch.as_tensor(np.ascontiguousarray(values))
+    values = values.to(device=dev, dtype=dtype)
+    n = int(n_samples) if n_samples is not None else (values.numel() if values.dim() == 1 else None)
+    if n is None:
+        raise ValueError("n_samples is required for batched values")
+    values, n_batch, layout_code = _values_layout(values, n, layout)
+    with torch.cuda.device(dev):
+        out = torch.empty((n_batch, m) if values.dim() == 2 else (m,), dtype=dtype, device=dev)
+        fn = lib.cmx_idw_apply_f64 if dtype == torch.float64 else lib.cmx_idw_apply_f32
+        rc = fn(_ptr(idx.contiguous()), _ptr(dist.contiguous()), m, k_table, _ptr(values), n, n_batch, layout_code,
+                k, int(k_min), float(power), _ptr(out), _stream())
+    _lib.check(rc, "cmx_idw_apply")
+    return out
+
+
+def empirical_variogram(x, y, z, nlags: int, *, geographic: bool = False):
+    """pykrige ``_initialize_variogram_model`` binning on the device.
+
+    Returns ``(lags, semivariance)`` NumPy arrays with empty bins dropped, plus the
+    raw dict (dmin, dmax, edges, sum_d, sum_g, count).  SURVEY.md Appendix A.1 step 3.
+    """
+    lib = _lib.load()
+    dev = _require_cuda(x.device if isinstance(x, torch.Tensor) else None)
+    x, y, z = _as_f64(x, dev), _as_f64(y, dev), _as_f64(z, dev)
+    n = x.numel()
+    metric = _lib.METRIC_GEOGRAPHIC if geographic else _lib.METRIC_EUCLIDEAN
+    nlags = int(nlags)
+    with torch.cuda.device(dev):
+        mm = torch.empty(2, dtype=torch.float64, device=dev)
+        _lib.check(lib.cmx_variogram_minmax(_ptr(x), _ptr(y), n, metric, _ptr(mm), _stream()), "cmx_variogram_minmax")
+        dmin, dmax = (float(v) for v in mm.cpu())
+        # bin edges exactly as pykrige builds them (python floats): dmin + n*dd, last edge dmax + 0.001
+        dd = (dmax - dmin) / nlags
+        edges = [dmin + i * dd for i in range(nlags)] + [dmax + 0.001]
+        edges_t = torch.tensor(edges, dtype=torch.float64, device=dev)
+        sums = torch.zeros((2, nlags), dtype=torch.float64, device=dev)
+        count = torch.zeros(nlags, dtype=torch.int64, device=dev)
+        _lib.check(lib.cmx_variogram_bins(_ptr(x), _ptr(y), _ptr(z), n, metric, nlags, _ptr(edges_t), _ptr(sums[0]),
+                                          _ptr(sums[1]), _ptr(count), _stream()), "cmx_variogram_bins")
+        sums_h = sums.cpu().numpy()
+        count_h = count.cpu().numpy()
+    good = count_h > 0
+    lags = sums_h[0][good] / count_h[good]
+    semivariance = sums_h[1][good] / count_h[good]
+    raw = dict(dmin=dmin, dmax=dmax, edges=np.array(edges), sum_d=sums_h[0], sum_g=sums_h[1], count=count_h)
+    return lags, semivariance, raw
+
+
+def ok_moving_window(s_x, s_y, z, t_x, t_y, grid: bool, *, k: int, variogram_model: str, params,
+                     geographic: bool = False, exact_values: bool = True, out_scale: float = 1.0,
+                     out_shift: float = 0.0, dtype: torch.dtype = torch.float64, return_sigmasq: bool = False):
+    """Moving-window ordinary kriging in the (already normalised / anisotropy-adjusted) frame.
+
+    pykrige ``execute(style, xpoints, ypoints, backend="loop", n_closest_points=k)``.
+    Grid targets: x = columns (n_x), y = rows (n_y); output (n_y * n_x,).
+    """
+    lib = _lib.load()
+    dev = _require_cuda(s_x.device if isinstance(s_x, torch.Tensor) else None)
+    s_x, s_y = _as_f64(s_x, dev), _as_f64(s_y, dev)
+    t_x, t_y = _as_f64(t_x, dev), _as_f64(t_y, dev)
+    if not isinstance(z, torch.Tensor):
+        z = torch.as_tensor(np.ascontiguousarray(z))
+    z = z.to(device=dev, dtype=dtype).contiguous()
+    n = s_x.numel()
+    m = t_x.numel() * t_y.numel() if grid else t_x.numel()
+    if not grid and t_x.numel() != t_y.numel():
+        raise ValueError("xpoints and ypoints must have same dimensions when treated as listing discrete points.")
+    model = _lib.VARIOGRAM_MODELS[variogram_model]
+    p = (ctypes.c_double * 3)(*[float(v) for v in list(params) + [0.0] * (3 - len(params))])
+    k = int(k)
+    with torch.cuda.device(dev):
+        out = torch.empty(m, dtype=dtype, device=dev)
+        sig = torch.empty(m, dtype=dtype, device=dev) if return_sigmasq else None
+        nsing = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws = _workspace(lib.cmx_ok_workspace_bytes(max(1, min(k, _lib.MAX_K)), m), dev)
+        fn = lib.cmx_ok_mw_f64 if dtype == torch.float64 else lib.cmx_ok_mw_f32
+        rc = fn(_ptr(s_x), _ptr(s_y), _ptr(z), n, _ptr(t_x), t_x.numel(), _ptr(t_y), t_y.numel(), int(grid),
+                _lib.METRIC_GEOGRAPHIC if geographic else _lib.METRIC_EUCLIDEAN, k, model, p, int(exact_values),
+                float(out_scale), float(out_shift), _ptr(out), _ptr(sig), _ptr(nsing), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "cmx_ok_mw")
+    if return_sigmasq:
+        return out, sig, nsing
+    return out, nsing

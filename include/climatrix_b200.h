@@ -1,0 +1,187 @@
+/*
+ * climatrix_b200 -- C ABI of the B200-native IDW / ordinary-kriging
+ * reconstruction hot path (libclimatrix_b200.so, sm_100a).
+ *
+ * Drop-in boundary.  The reference (jamesWalczak/climatrix) is pure Python: its
+ * hot path calls third-party native code through Python bindings.  Each entry
+ * point below replaces one of those call sites; the Python host layer
+ * (climatrix_b200/*.py) and any other FFI (ctypes stub in INTEGRATION.md) bind
+ * exactly these symbols.
+ *
+ *   cmx_knn            <- scipy.spatial.cKDTree(points).query(q, k, workers=-1)
+ *                         src/climatrix/reconstruct/idw.py:155-158
+ *                         (and pykrige's moving-window tree.query)
+ *   cmx_idw_f64/_f32   <- the kd-tree query + NumPy weighting epilogue
+ *                         src/climatrix/reconstruct/idw.py:155-180
+ *   cmx_idw_apply_*    <- idw.py:163-180 re-applied to a stored neighbour table
+ *                         (HPO inner loop, src/climatrix/optim/bayesian.py:399-405)
+ *   cmx_variogram_*    <- pykrige core._initialize_variogram_model (pdist + binning),
+ *                         reached from src/climatrix/reconstruct/kriging.py:215-224
+ *   cmx_ok_mw_f64/_f32 <- pykrige OrdinaryKriging.execute(backend="loop",
+ *                         n_closest_points=k), call site kriging.py:236-241
+ *
+ * Conventions
+ *  - All data pointers are DEVICE pointers owned by the caller; nothing is
+ *    allocated or freed inside.  Scratch comes from a caller-provided
+ *    workspace (size from the matching *_workspace_bytes()).
+ *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it.
+ *  - Return value: CMX_OK (0) or a negative CMX_ERR_* code.  Nothing throws
+ *    across the ABI.  cmx_strerror() maps codes to text.
+ *  - Coordinates are always float64 (neighbour sets must match the reference's
+ *    float64 kd-tree bit-exactly); `_f32`/`_f64` names the dtype of sample
+ *    values and of the reconstructed field.
+ *  - Targets: `target_is_grid != 0` -> dense grid, `t_a` is the latitude axis
+ *    (n_a rows), `t_b` the longitude axis (n_b columns), target m = i*n_b + j
+ *    (row-major, the order of DenseDomain.get_all_spatial_points,
+ *    src/climatrix/dataset/domain.py:917-922).  Otherwise explicit points:
+ *    `t_a[m], t_b[m]`, n_a == n_b == M (SparseDomain, domain.py:738).
+ *  - Neighbour order and ties: ascending by (squared distance, sample index),
+ *    squared distance = dx*dx + dy*dy in float64 without FMA contraction.
+ */
+#ifndef CLIMATRIX_B200_H
+#define CLIMATRIX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMX_OK 0
+#define CMX_ERR_BAD_ARG (-1)        /* null pointer, negative size, k < 1 ...            */
+#define CMX_ERR_K_GT_N (-2)         /* more neighbours requested than samples             */
+#define CMX_ERR_K_TOO_LARGE (-3)    /* k above CMX_MAX_K                                  */
+#define CMX_ERR_WORKSPACE (-4)      /* workspace missing or too small                     */
+#define CMX_ERR_CUDA (-5)           /* a CUDA runtime call or launch failed               */
+#define CMX_ERR_UNSUPPORTED (-6)    /* option not implemented (e.g. unknown variogram)    */
+#define CMX_ERR_TOO_MANY (-7)       /* more than 2^31-1 samples or targets                */
+
+#define CMX_MAX_K 128
+
+/* variogram models, pykrige/variogram_models.py (params: see cmx_ok_mw_*) */
+#define CMX_VARIOGRAM_LINEAR 0
+#define CMX_VARIOGRAM_POWER 1
+#define CMX_VARIOGRAM_GAUSSIAN 2
+#define CMX_VARIOGRAM_SPHERICAL 3
+#define CMX_VARIOGRAM_EXPONENTIAL 4
+
+/* distance metric of the kriging frame (pykrige coordinates_type) */
+#define CMX_METRIC_EUCLIDEAN 0
+#define CMX_METRIC_GEOGRAPHIC 1
+
+/* layout of a [batch x samples] value matrix */
+#define CMX_LAYOUT_BATCH_MAJOR 0  /* vals[t * n + i]  (time, point)  */
+#define CMX_LAYOUT_SAMPLE_MAJOR 1 /* vals[i * n_batch + t]  (point, time) -- the fast one */
+
+int cmx_version(void);
+const char* cmx_strerror(int code);
+/* last CUDA error text recorded by this library on the calling thread ("" if none) */
+const char* cmx_last_cuda_error(void);
+
+/* ---- k nearest neighbours (brute force, fp32 filter + fp64 exact re-rank) ---- */
+
+/* Scratch bytes cmx_knn / cmx_idw_* / cmx_ok_mw_* need for `k` on the current device. */
+size_t cmx_knn_workspace_bytes(int k);
+
+/*
+ * idx_out  [M][k] int32   sample indices, ascending by (dist, index)      (required)
+ * dist_out [M][k] float64 Euclidean distances sqrt(dx*dx+dy*dy)           (may be NULL)
+ * Replaces cKDTree(points).query(queries, k): idw.py:155-158.
+ */
+int cmx_knn(const double* s_a, const double* s_b, int64_t n_samples,
+            const double* t_a, int64_t n_a, const double* t_b, int64_t n_b, int target_is_grid,
+            int k, int32_t* idx_out, double* dist_out,
+            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- inverse distance weighting ---- */
+
+/* Extra scratch (beyond cmx_knn_workspace_bytes) for n_batch > 1: the [M][k] weight table. */
+size_t cmx_idw_workspace_bytes(int k, int64_t n_targets, int64_t n_batch);
+
+/*
+ * out[t*M + m] = IDW estimate of slice t at target m (NaN where fewer than k_min
+ * finite neighbours): idw.py:155-180, looped over the batch (the reference rejects
+ * dynamic datasets, idw.py:87-104, so a batch is n_batch static calls).
+ * idx_out/dist_out: optional [M][k] neighbour table (NULL to skip).
+ */
+int cmx_idw_f64(const double* s_lat, const double* s_lon, int64_t n_samples,
+                const double* vals, int64_t n_batch, int vals_layout,
+                const double* t_lat, int64_t n_lat, const double* t_lon, int64_t n_lon, int target_is_grid,
+                int k, int k_min, double power,
+                double* out, int32_t* idx_out, double* dist_out,
+                void* workspace, size_t workspace_bytes, void* stream);
+int cmx_idw_f32(const double* s_lat, const double* s_lon, int64_t n_samples,
+                const float* vals, int64_t n_batch, int vals_layout,
+                const double* t_lat, int64_t n_lat, const double* t_lon, int64_t n_lon, int target_is_grid,
+                int k, int k_min, double power,
+                float* out, int32_t* idx_out, double* dist_out,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Re-apply idw.py:163-180 to a stored neighbour table with other (k_use <= k_table,
+ * power, k_min): the hyper-parameter search inner loop (optim/bayesian.py:399-405).
+ */
+int cmx_idw_apply_f64(const int32_t* idx, const double* dist, int64_t n_targets, int k_table,
+                      const double* vals, int64_t n_samples, int64_t n_batch, int vals_layout,
+                      int k_use, int k_min, double power, double* out, void* stream);
+int cmx_idw_apply_f32(const int32_t* idx, const double* dist, int64_t n_targets, int k_table,
+                      const float* vals, int64_t n_samples, int64_t n_batch, int vals_layout,
+                      int k_use, int k_min, double power, float* out, void* stream);
+
+/* ---- empirical variogram (pykrige core._initialize_variogram_model) ---- */
+
+/* minmax[0] = min, minmax[1] = max pair distance over all i>j pairs (device, 2 doubles). */
+int cmx_variogram_minmax(const double* x, const double* y, int64_t n, int metric,
+                         double* minmax, void* stream);
+/*
+ * edges[nlags+1] (device): bin n holds pairs with edges[n] <= d < edges[n+1].
+ * sum_d / sum_g / count [nlags] (device) are ACCUMULATED into (zero them first);
+ * g = 0.5 * (z_i - z_j)^2.
+ */
+int cmx_variogram_bins(const double* x, const double* y, const double* z, int64_t n, int metric,
+                       int nlags, const double* edges,
+                       double* sum_d, double* sum_g, unsigned long long* count, void* stream);
+
+/* ---- ordinary kriging, moving window ---- */
+
+/*
+ * Per target: k nearest samples in the kriging frame (x, y already normalised and
+ * anisotropy-adjusted; CMX_METRIC_GEOGRAPHIC: x = lon, y = lat in degrees, neighbours
+ * by 3-D chord, distances great-circle degrees), assemble the (k+1)x(k+1) system
+ * A = [[-gamma(D), 1], [1^T, 0]] (zero diagonal), b = [-gamma(d); 1] with entries
+ * forced to 0 where d <= 1e-10 (exact_values), solve by LU with partial pivoting in
+ * float64, z = sum_i x_i Z_i, sigmasq = -x.b.   pykrige ok.py
+ * _exec_loop_moving_window, reached from kriging.py:236-241.
+ * params: linear [slope, nugget, -]; power [scale, exponent, nugget];
+ *         gaussian/spherical/exponential [psill, range, nugget].
+ * out[m] = z * out_scale + out_shift: the de-standardisation of kriging.py:245 fused into
+ * the store (pass 1, 0 for plain pykrige output).
+ * out [M] (required), sigmasq_out [M] (may be NULL); NaN + *n_singular++ where the
+ * local system is singular (duplicate neighbours; the reference raises LinAlgError).
+ */
+int cmx_ok_mw_f64(const double* s_x, const double* s_y, const double* z, int64_t n_samples,
+                  const double* t_x, int64_t n_x, const double* t_y, int64_t n_y, int target_is_grid,
+                  int metric, int k, int variogram_model, const double params[3], int exact_values,
+                  double out_scale, double out_shift,
+                  double* out, double* sigmasq_out, int32_t* n_singular,
+                  void* workspace, size_t workspace_bytes, void* stream);
+int cmx_ok_mw_f32(const double* s_x, const double* s_y, const float* z, int64_t n_samples,
+                  const double* t_x, int64_t n_x, const double* t_y, int64_t n_y, int target_is_grid,
+                  int metric, int k, int variogram_model, const double params[3], int exact_values,
+                  double out_scale, double out_shift,
+                  float* out, float* sigmasq_out, int32_t* n_singular,
+                  void* workspace, size_t workspace_bytes, void* stream);
+/* total scratch for cmx_ok_mw_* (includes the kNN scratch) */
+size_t cmx_ok_workspace_bytes(int k, int64_t n_targets);
+
+/* ---- instrumentation ---- */
+
+/* Kernels launched by this library on the calling thread since the last reset. */
+int64_t cmx_launch_count(void);
+void cmx_reset_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIMATRIX_B200_H */
