@@ -1,7 +1,60 @@
 """climatrix_b200 -- B200-native IDW / ordinary-kriging reconstruction (one hot path of climatrix).
 
-Hand-written sm_100a CUDA behind a C ABI (``include/climatrix_b200.h``), a Python
-host layer that mirrors climatrix's reconstructor plug-in API.  No CPU fallback.
+Hand-written sm_100a CUDA behind a C ABI (``include/climatrix_b200.h``) and a Python
+host layer that mirrors climatrix's reconstructor plug-in API: ``method="idw"`` and
+``method="ok"`` are drop-ins.  No CPU fallback: without the built library or a CUDA
+device the reconstructors raise.
+
+    from climatrix_b200 import BaseClimatrixDataset, Domain, FieldArray
+    sparse = BaseClimatrixDataset(FieldArray(values, ("point",), {"latitude": ("point", lat), ...}))
+    dense = sparse.reconstruct(Domain.from_lat_lon(lat=..., lon=..., kind="dense"), method="idw", k=32)
 """
 
 __version__ = "0.1.0"
+
+from .dataset import (  # noqa: F401
+    Axis,
+    AxisType,
+    BaseClimatrixDataset,
+    DenseDomain,
+    Domain,
+    FieldArray,
+    SparseDomain,
+    register_xarray_accessor,
+)
+from .exceptions import (  # noqa: F401
+    OperationNotSupportedForDynamicDatasetError,
+    ReconstructorConfigurationFailed,
+)
+from .plugin import BaseReconstructor, Hyperparameter, ReconstructionType  # noqa: F401
+from .idw import IDWReconstructor  # noqa: F401
+from .kriging import OrdinaryKrigingReconstructor  # noqa: F401
+
+
+def install_into_climatrix() -> bool:
+    """Register the GPU reconstructors in a real climatrix installation.
+
+    climatrix resolves ``method=`` through ``ReconstructionType``, an Enum snapshotted
+    from ``BaseReconstructor._registry`` at first import (reconstruct/type.py:8-11), so the
+    registry entry is replaced *and* the enum is rebuilt.  Returns False when climatrix
+    is not importable.
+    """
+    try:
+        import climatrix.reconstruct.base as ref_base  # type: ignore
+        import climatrix.reconstruct.type as ref_type  # type: ignore
+    except Exception:  # noqa: BLE001
+        return False
+    import enum
+
+    ref_base.BaseReconstructor._registry["idw"] = IDWReconstructor
+    ref_base.BaseReconstructor._registry["ok"] = OrdinaryKrigingReconstructor
+    members = {name.upper(): cls for name, cls in ref_base.BaseReconstructor._registry.items()}
+    new_enum = enum.Enum("ReconstructionType", members)
+    for attr in ("get", "list", "__missing__"):
+        if hasattr(ref_type.ReconstructionType, attr):
+            setattr(new_enum, attr, getattr(ref_type.ReconstructionType, attr))
+    ref_type.ReconstructionType = new_enum
+    return True
+
+
+register_xarray_accessor()

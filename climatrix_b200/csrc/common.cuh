@@ -116,6 +116,25 @@ __device__ __forceinline__ double idw_raw_weight(double d2, double power) {
     return idw_weight_from_dist(sqrt(d2), power);
 }
 
+__device__ __forceinline__ void atomic_min_double(double* addr, double v) {
+    unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+    unsigned long long old = *a;
+    while (__longlong_as_double((long long)old) > v) {
+        const unsigned long long prev = atomicCAS(a, old, (unsigned long long)__double_as_longlong(v));
+        if (prev == old) break;
+        old = prev;
+    }
+}
+__device__ __forceinline__ void atomic_max_double(double* addr, double v) {
+    unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+    unsigned long long old = *a;
+    while (__longlong_as_double((long long)old) < v) {
+        const unsigned long long prev = atomicCAS(a, old, (unsigned long long)__double_as_longlong(v));
+        if (prev == old) break;
+        old = prev;
+    }
+}
+
 template <typename V>
 __device__ __forceinline__ V quiet_nan();
 template <>

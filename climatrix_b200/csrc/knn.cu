@@ -5,17 +5,22 @@
 // idw.py:163-180.
 //
 // Scheme (see DESIGN.md "K1"):
-//   * every (target, sample) pair is evaluated on the FP32 pipe in the expanded
-//     form  t = |s|^2 - 2 q.s  (2 FFMA + 1 compare per pair) in coordinates
-//     centred on the target tile, against a per-target threshold held in a
-//     register;
+//   * every (target, sample) pair is evaluated on the FP32 pipe in the expanded form
+//     t = |s|^2 - 2 q.s  in coordinates centred on the target tile: two packed
+//     FFMA2 (fma.rn.f32x2) per two pairs, reduced with the 3-input FMNMX3 to a
+//     running minimum per target over a group of 32 samples; one compare per target
+//     and group against a threshold held in a register;
 //   * samples are staged through shared memory by TMA bulk copies
 //     (cp.async.bulk + mbarrier), re-centred and converted to fp32 per tile;
-//   * pairs that pass the (conservative, error-bounded) fp32 filter are pushed to
-//     a per-target candidate buffer; when a buffer fills, the warp re-ranks it
-//     cooperatively in exact, non-contracted float64 (bit-identical to cKDTree's
-//     dx*dx+dy*dy) with a bitonic sort/merge over warp shuffles and tightens the
-//     threshold.  Ties break by sample index, so results are deterministic;
+//   * a group whose minimum passes the (conservative, error-bounded) fp32 filter is
+//     re-examined by the whole warp (one sample per lane, ballot-compacted pushes
+//     into the target's candidate buffer); when a buffer fills, the warp re-ranks
+//     it in exact, non-contracted float64 (bit-identical to cKDTree's dx*dx+dy*dy)
+//     with a bitonic sort/merge over warp shuffles and tightens the threshold.
+//     Ties break by sample index, so results are deterministic;
+//   * thresholds start from a rigorous upper bound on the k-th neighbour distance
+//     read off a summed-area table of sample counts (built by four tiny pre-pass
+//     kernels), so a target sees ~2-3k candidates instead of ~k ln(N/k);
 //   * the final re-rank leaves the k neighbours in registers, where the IDW
 //     weights and the weighted mean are evaluated before anything is stored.
 #include <limits.h>
@@ -28,14 +33,25 @@ namespace {
 constexpr int WARPS = 4;
 constexpr int THREADS = WARPS * 32;
 constexpr int TS = 2048;             // samples per shared-memory stage
-constexpr int CHK = 32;              // samples between candidate-buffer checks
+constexpr int GRP = 32;              // samples per filter group (= one per lane in the re-examination)
 constexpr int CAP = 64;              // candidate slots per target
-constexpr int FLUSH_AT = CAP - CHK;  // re-rank a target once it holds more than this
+constexpr int FLUSH_AT = CAP - GRP;  // re-rank a target once it holds more than this
 constexpr int MAX_CTAS_PER_SM = 2;
-constexpr int MAX_TQ = WARPS * 8 * 32;
+constexpr int MAX_QPT = 8;
+constexpr int MAX_TQ = WARPS * MAX_QPT * 32;
+constexpr int GMAX = 1024;           // seed grid: at most GMAX x GMAX cells
+constexpr int SAT_LD = GMAX + 1;     // row stride of the summed-area table
 
 #define CMX_INF __longlong_as_double(0x7ff0000000000000LL)
 #define CMX_INF_F __int_as_float(0x7f800000)
+
+// geometry of the sample-count grid (device resident, written by seed_geometry_kernel)
+struct SeedGrid {
+    double a0, b0, h, inv_h;
+    int ga, gb;
+    int valid;
+    int pad;
+};
 
 struct KnnArgs {
     KnnJob j;
@@ -46,8 +62,149 @@ struct KnnArgs {
     unsigned* cand; // [ctas][TQ][CAP] candidate sample indices
     double* list_d; // [ctas][TQ][KP]  running top-KP squared distances (ascending)
     int* list_i;    // [ctas][TQ][KP]  and their sample indices
+    const SeedGrid* seed;
+    const int* sat; // (GMAX+1)^2 summed-area table of sample counts (exclusive prefix)
 };
 
+// ------------------------------------------------------------------------------------------
+// seed grid pre-pass
+// ------------------------------------------------------------------------------------------
+__global__ void seed_init_kernel(double* bbox) {
+    bbox[0] = CMX_INF;
+    bbox[1] = -CMX_INF;
+    bbox[2] = CMX_INF;
+    bbox[3] = -CMX_INF;
+}
+
+__global__ void seed_bbox_kernel(const double* __restrict__ sa, const double* __restrict__ sb, long long n,
+                                 double* bbox) {
+    double lo_a = CMX_INF, hi_a = -CMX_INF, lo_b = CMX_INF, hi_b = -CMX_INF;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double a = sa[i], b = sb[i];
+        if (isfinite(a) && isfinite(b)) {
+            lo_a = fmin(lo_a, a);
+            hi_a = fmax(hi_a, a);
+            lo_b = fmin(lo_b, b);
+            hi_b = fmax(hi_b, b);
+        }
+    }
+    lo_a = warp_min(lo_a);
+    hi_a = warp_max(hi_a);
+    lo_b = warp_min(lo_b);
+    hi_b = warp_max(hi_b);
+    if ((threadIdx.x & 31) == 0 && lo_a <= hi_a) {
+        atomic_min_double(&bbox[0], lo_a);
+        atomic_max_double(&bbox[1], hi_a);
+        atomic_min_double(&bbox[2], lo_b);
+        atomic_max_double(&bbox[3], hi_b);
+    }
+}
+
+__global__ void seed_geometry_kernel(const double* bbox, long long n, SeedGrid* g) {
+    const double ea = bbox[1] - bbox[0], eb = bbox[3] - bbox[2];
+    SeedGrid s;
+    s.a0 = bbox[0];
+    s.b0 = bbox[2];
+    s.valid = (ea >= 0.0 && eb >= 0.0 && isfinite(ea) && isfinite(eb)) ? 1 : 0;
+    // about two samples per cell, at most GMAX cells per axis
+    double h = 0.0;
+    if (s.valid) {
+        const double area = (ea > 0 ? ea : 1.0) * (eb > 0 ? eb : 1.0);
+        h = sqrt(2.0 * area / (double)(n > 0 ? n : 1));
+        h = fmax(h, fmax(ea, eb) / (double)(GMAX - 1));
+        if (!(h > 0.0)) h = 1.0;
+    } else {
+        h = 1.0;
+    }
+    s.h = h;
+    s.inv_h = 1.0 / h;
+    int ga = (int)(ea * s.inv_h) + 1, gb = (int)(eb * s.inv_h) + 1;
+    s.ga = ga < 1 ? 1 : (ga > GMAX ? GMAX : ga);
+    s.gb = gb < 1 ? 1 : (gb > GMAX ? GMAX : gb);
+    s.pad = 0;
+    *g = s;
+}
+
+__device__ __forceinline__ int seed_cell(double x, double x0, double inv_h, int g) {
+    int c = (int)floor((x - x0) * inv_h);
+    return c < 0 ? 0 : (c > g - 1 ? g - 1 : c);
+}
+
+__global__ void seed_hist_kernel(const double* __restrict__ sa, const double* __restrict__ sb, long long n,
+                                 const SeedGrid* g, int* sat) {
+    const SeedGrid s = *g;
+    if (!s.valid) return;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double a = sa[i], b = sb[i];
+        if (isfinite(a) && isfinite(b)) {
+            const int ia = seed_cell(a, s.a0, s.inv_h, s.ga), ib = seed_cell(b, s.b0, s.inv_h, s.gb);
+            atomicAdd(&sat[(size_t)(ia + 1) * SAT_LD + (ib + 1)], 1);
+        }
+    }
+}
+
+// inclusive scan along b of row r = blockIdx.x + 1 (one warp per row)
+__global__ void seed_rowscan_kernel(const SeedGrid* g, int* sat) {
+    const int ga = g->ga, gb = g->gb;
+    const int r = blockIdx.x + 1;
+    if (r > ga) return;
+    int* row = sat + (size_t)r * SAT_LD;
+    const int lane = threadIdx.x;
+    int carry = 0;
+    for (int c0 = 1; c0 <= gb; c0 += 32) {
+        const int c = c0 + lane;
+        int v = c <= gb ? row[c] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(kFull, v, o);
+            if (lane >= o) v += u;
+        }
+        v += carry;
+        if (c <= gb) row[c] = v;
+        carry = __shfl_sync(kFull, v, 31);
+    }
+}
+
+// inclusive scan along a of every column (thread per column)
+__global__ void seed_colscan_kernel(const SeedGrid* g, int* sat) {
+    const int ga = g->ga, gb = g->gb;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (c > gb) return;
+    int acc = 0;
+    for (int r = 1; r <= ga; ++r) {
+        acc += sat[(size_t)r * SAT_LD + c];
+        sat[(size_t)r * SAT_LD + c] = acc;
+    }
+}
+
+// Rigorous upper bound on the squared distance from (ta, tb) to its k-th nearest sample:
+// grow a box of cells around the target's cell until it holds >= k samples; every one of
+// them is no farther than the farthest corner of that box.
+__device__ __forceinline__ double seed_bound_d2(const SeedGrid& s, const int* __restrict__ sat, double ta,
+                                                double tb, int k) {
+    if (!s.valid) return CMX_INF;
+    const int ia = seed_cell(ta, s.a0, s.inv_h, s.ga), ib = seed_cell(tb, s.b0, s.inv_h, s.gb);
+    const int wmax = max(s.ga, s.gb);
+    for (int w = 0;; w = w < 8 ? w + 1 : w * 2) {
+        const int la = max(ia - w, 0), ha = min(ia + w, s.ga - 1);
+        const int lb = max(ib - w, 0), hb = min(ib + w, s.gb - 1);
+        const int cnt = sat[(size_t)(ha + 1) * SAT_LD + (hb + 1)] - sat[(size_t)la * SAT_LD + (hb + 1)] -
+                        sat[(size_t)(ha + 1) * SAT_LD + lb] + sat[(size_t)la * SAT_LD + lb];
+        if (cnt >= k) {
+            const double A_lo = s.a0 + la * s.h, A_hi = s.a0 + (ha + 1) * s.h;
+            const double B_lo = s.b0 + lb * s.h, B_hi = s.b0 + (hb + 1) * s.h;
+            const double slack = 1e-9 * (s.h + fabs(A_lo) + fabs(A_hi) + fabs(B_lo) + fabs(B_hi));
+            const double da = fmax(fabs(ta - A_lo), fabs(A_hi - ta)) + slack;
+            const double db = fmax(fabs(tb - B_lo), fabs(B_hi - tb)) + slack;
+            return (da * da + db * db) * (1.0 + 1e-9);
+        }
+        if (w >= wmax) return CMX_INF;  // fewer than k finite samples in total
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// exact re-rank machinery
+// ------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool lex_less(double da, int ia, double db, int ib) {
     return da < db || (da == db && ia < ib);
 }
@@ -252,6 +409,25 @@ __device__ __noinline__ double rerank_target(const KnnArgs& a, int lane, long lo
     return num / den;
 }
 
+// two IEEE FMAs in one instruction (FFMA2): r = q * (x0, x1) + (c0, c1), q broadcast
+__device__ __forceinline__ void fma2_bcast(float q, float x0, float x1, float c0, float c1, float& r0, float& r1) {
+    asm("{\n"
+        ".reg .b64 qa, xx, cc, rr;\n"
+        "mov.b64 qa, {%2, %2};\n"
+        "mov.b64 xx, {%3, %4};\n"
+        "mov.b64 cc, {%5, %6};\n"
+        "fma.rn.f32x2 rr, qa, xx, cc;\n"
+        "mov.b64 {%0, %1}, rr;\n"
+        "}"
+        : "=f"(r0), "=f"(r1)
+        : "f"(q), "f"(x0), "f"(x1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ float min3f(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));  // FMNMX3; NaN operands are ignored
+    return d;
+}
+
 template <int E, int QPT>
 __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __grid_constant__ KnnArgs a) {
     constexpr int TQ = WARPS * QPT * 32;
@@ -265,6 +441,7 @@ __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __g
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
     if (tid == 0) {
         mbar_init(&mbar, 1);
         mbar_fence_init();
@@ -274,7 +451,7 @@ __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __g
     const long long n = a.j.n;
     const int n_st = (int)((n + TS - 1) / TS);
     const long long slot0 = (long long)blockIdx.x * TQ + (long long)(warp * QPT) * 32;  // + q*32 + lane
-    unsigned* const mycand = a.cand + (slot0 + lane) * CAP;
+    const SeedGrid seed = *a.seed;
 
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
         // ---------------- targets of this thread ----------------
@@ -321,41 +498,25 @@ __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __g
 #pragma unroll
             for (int q = 0; q < QPT; ++q) {
                 const bool ok = (validm >> q) & 1u;
-                Qa[q] = ok ? -2.0f * __double2float_rn(__dsub_rn(ta[q], ca)) : 0.0f;
-                Qb[q] = ok ? -2.0f * __double2float_rn(__dsub_rn(tb[q], cb)) : 0.0f;
-                thr[q] = ok ? CMX_INF_F : -CMX_INF_F;
+                const float qa = __double2float_rn(__dsub_rn(ta[q], ca));
+                const float qb = __double2float_rn(__dsub_rn(tb[q], cb));
+                Qa[q] = ok ? -2.0f * qa : 0.0f;
+                Qb[q] = ok ? -2.0f * qb : 0.0f;
+                // rigorous starting threshold from the sample-count grid (never below the true k-th distance)
+                thr[q] = ok ? filter_threshold(seed_bound_d2(seed, a.sat, ta[q], tb[q], a.j.k), qa, qb) : -CMX_INF_F;
                 off[q] = 0;
             }
         }
 
-        // warp-cooperative re-rank of every target of this warp selected by `pick`
-        auto rerank_pass = [&](bool final, double* res) {
-#pragma unroll
-            for (int q = 0; q < QPT; ++q) {
-                unsigned need = __ballot_sync(kFull, final ? ((validm >> q) & 1u) != 0 : off[q] > FLUSH_AT);
-                while (need) {
-                    const int L = __ffs(need) - 1;
-                    need &= need - 1;
-                    const int cnt = __shfl_sync(kFull, off[q], L);
-                    const bool has = (__shfl_sync(kFull, has_list, L) >> q) & 1u;
-                    const int ts = (warp * QPT + q) * 32 + L;
-                    double ta = 0.0, tb = 0.0;
-                    long long m = 0;
-                    target_coords<QPT>(a, tile, ts, ta, tb, m);
-                    const float qa = __double2float_rn(__dsub_rn(ta, ca));
-                    const float qb = __double2float_rn(__dsub_rn(tb, cb));
-                    const double r = rerank_target<E>(a, lane, slot0 + q * 32 + L, ta, tb, m, qa, qb, cnt, has, final);
-                    if (lane == L) {
-                        if (final) {
-                            res[q] = r;
-                        } else {
-                            thr[q] = (float)r;
-                            off[q] = 0;
-                            has_list |= 1u << q;
-                        }
-                    }
-                }
-            }
+        // exact re-rank of target (lane L, slot q) of this warp; returns threshold or fused value
+        auto rerank = [&](int q, int L, int cnt, bool has, bool final) -> double {
+            const int ts = (warp * QPT + q) * 32 + L;
+            double ta = 0.0, tb = 0.0;
+            long long m = 0;
+            target_coords<QPT>(a, tile, ts, ta, tb, m);
+            const float qa = __double2float_rn(__dsub_rn(ta, ca));
+            const float qb = __double2float_rn(__dsub_rn(tb, cb));
+            return rerank_target<E>(a, lane, slot0 + q * 32 + L, ta, tb, m, qa, qb, cnt, has, final);
         };
 
         // ---------------- sweep over all samples ----------------
@@ -401,52 +562,86 @@ __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __g
                 tma_load_1d(raw_b, a.j.s_b + base + TS, TS * 8u, &mbar);
             }
 
-            const int cnt_pad = (cntS + CHK - 1) & ~(CHK - 1);
+            const int cnt_pad = (cntS + GRP - 1) & ~(GRP - 1);
             const unsigned jbase = (unsigned)base;
 #pragma unroll 1
-            for (int c0 = 0; c0 < cnt_pad; c0 += CHK) {
+            for (int g0 = 0; g0 < cnt_pad; g0 += GRP) {
+                // ---- filter: running minimum of t per target over the group (FP32 pipe) ----
+                float mn[QPT];
 #pragma unroll
-                for (int j = 0; j < CHK; j += 4) {
-                    const float4 A4 = *reinterpret_cast<const float4*>(cA + c0 + j);
-                    const float4 B4 = *reinterpret_cast<const float4*>(cB + c0 + j);
-                    const float4 S4 = *reinterpret_cast<const float4*>(cS + c0 + j);
-                    const float xa[4] = {A4.x, A4.y, A4.z, A4.w};
-                    const float xb[4] = {B4.x, B4.y, B4.z, B4.w};
-                    const float xs[4] = {S4.x, S4.y, S4.z, S4.w};
+                for (int q = 0; q < QPT; ++q) mn[q] = CMX_INF_F;
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) {
-                        float t[QPT];
-                        bool any = false;
+                for (int j = 0; j < GRP; j += 4) {
+                    const float4 A4 = *reinterpret_cast<const float4*>(cA + g0 + j);
+                    const float4 B4 = *reinterpret_cast<const float4*>(cB + g0 + j);
+                    const float4 S4 = *reinterpret_cast<const float4*>(cS + g0 + j);
 #pragma unroll
-                        for (int q = 0; q < QPT; ++q) {
-                            t[q] = fmaf(Qa[q], xa[s], fmaf(Qb[q], xb[s], xs[s]));
-                            any |= t[q] < thr[q];
-                        }
-                        if (any) {
-                            const unsigned jj = jbase + (unsigned)(c0 + j + s);
-#pragma unroll
-                            for (int q = 0; q < QPT; ++q) {
-                                if (t[q] < thr[q]) {
-                                    mycand[q * 32 * CAP + off[q]] = jj;
-                                    ++off[q];
-                                }
-                            }
-                        }
+                    for (int q = 0; q < QPT; ++q) {
+                        float u0, u1, u2, u3, t0, t1, t2, t3;
+                        fma2_bcast(Qb[q], B4.x, B4.y, S4.x, S4.y, u0, u1);
+                        fma2_bcast(Qb[q], B4.z, B4.w, S4.z, S4.w, u2, u3);
+                        fma2_bcast(Qa[q], A4.x, A4.y, u0, u1, t0, t1);
+                        fma2_bcast(Qa[q], A4.z, A4.w, u2, u3, t2, t3);
+                        mn[q] = min3f(min3f(mn[q], t0, t1), t2, t3);
                     }
                 }
-                int mx = off[0];
+                // ---- groups that may hold a neighbour: the warp re-examines them, one sample per lane ----
 #pragma unroll
-                for (int q = 1; q < QPT; ++q) mx = max(mx, off[q]);
-                if (__any_sync(kFull, mx > FLUSH_AT)) rerank_pass(false, nullptr);
+                for (int q = 0; q < QPT; ++q) {
+                    unsigned hit = __ballot_sync(kFull, mn[q] < thr[q]);
+                    if (hit) {
+                        const float xa = cA[g0 + lane], xb = cB[g0 + lane], xs = cS[g0 + lane];
+                        do {
+                            const int L = __ffs(hit) - 1;
+                            hit &= hit - 1;
+                            const float qa2 = __shfl_sync(kFull, Qa[q], L);
+                            const float qb2 = __shfl_sync(kFull, Qb[q], L);
+                            const float th = __shfl_sync(kFull, thr[q], L);
+                            const int o = __shfl_sync(kFull, off[q], L);
+                            const float t = fmaf(qa2, xa, fmaf(qb2, xb, xs));
+                            const bool pass = t < th;
+                            const unsigned pm = __ballot_sync(kFull, pass);
+                            const long long slot = slot0 + q * 32 + L;
+                            if (pass) a.cand[slot * CAP + o + __popc(pm & lt_mask)] = jbase + (unsigned)(g0 + lane);
+                            int no = o + __popc(pm);
+                            float nthr = th;
+                            const bool full = no > FLUSH_AT;
+                            if (full) {
+                                __syncwarp();
+                                const bool has = (__shfl_sync(kFull, has_list, L) >> q) & 1u;
+                                nthr = (float)rerank(q, L, no, has, false);
+                                no = 0;
+                            }
+                            if (lane == L) {
+                                off[q] = no;
+                                if (full) {
+                                    thr[q] = nthr;
+                                    has_list |= 1u << q;
+                                }
+                            }
+                        } while (hit);
+                    }
+                }
             }
             buf ^= 1;
         }
 
         // ---------------- final re-rank + epilogue ----------------
         double res[QPT];
+        __syncwarp();
 #pragma unroll
-        for (int q = 0; q < QPT; ++q) res[q] = 0.0;
-        rerank_pass(true, res);
+        for (int q = 0; q < QPT; ++q) {
+            res[q] = 0.0;
+            unsigned need = __ballot_sync(kFull, ((validm >> q) & 1u) != 0);
+            while (need) {
+                const int L = __ffs(need) - 1;
+                need &= need - 1;
+                const int cnt = __shfl_sync(kFull, off[q], L);
+                const bool has = (__shfl_sync(kFull, has_list, L) >> q) & 1u;
+                const double r = rerank(q, L, cnt, has, true);
+                if (lane == L) res[q] = r;
+            }
+        }
         if (a.j.idw_mode == 1) {
 #pragma unroll
             for (int q = 0; q < QPT; ++q) {
@@ -475,13 +670,15 @@ int launch(const KnnArgs& args, int ctas, cudaStream_t stream) {
 
 inline int list_slots(int k) { return k <= 32 ? 1 : (k <= 64 ? 2 : 4); }
 
+constexpr size_t SEED_BYTES = (512 + (size_t)SAT_LD * SAT_LD * sizeof(int) + 255) & ~size_t(255);
+
 }  // namespace
 
 size_t knn_workspace_bytes(int k) {
     if (k < 1 || k > CMX_MAX_K) return 0;
     const size_t ctas = (size_t)sm_count() * MAX_CTAS_PER_SM;
     const size_t kp = 32 * (size_t)list_slots(k);
-    return ctas * MAX_TQ * (CAP * sizeof(unsigned) + kp * (sizeof(double) + sizeof(int))) + 256;
+    return ctas * MAX_TQ * (CAP * sizeof(unsigned) + kp * (sizeof(double) + sizeof(int))) + SEED_BYTES + 512;
 }
 
 int run_knn(const KnnJob& job, cudaStream_t stream) {
@@ -493,7 +690,7 @@ int run_knn(const KnnJob& job, cudaStream_t stream) {
     if (job.idw_mode == 1 && (!job.vals || !job.out || job.k_min < 1)) return CMX_ERR_BAD_ARG;
     const long long M = job.grid ? job.n_a * job.n_b : job.n_a;
     if (M == 0) return CMX_OK;
-    if (job.n > 0x7fffffffLL || M > 0x7fffffffLL * 16LL) return CMX_ERR_TOO_MANY;
+    if (job.n > 0x7fffffffLL) return CMX_ERR_TOO_MANY;
     const size_t need = knn_workspace_bytes(job.k);
     if (!job.workspace || job.workspace_bytes < need) return CMX_ERR_WORKSPACE;
 
@@ -525,13 +722,33 @@ int run_knn(const KnnJob& job, cudaStream_t stream) {
     args.num_tiles = (int)tiles;
     const int ctas = (int)(tiles < slots ? tiles : slots);
 
+    // workspace: [seed grid | lists d | candidates | lists i]
     const size_t kp = 32 * (size_t)list_slots(job.k);
     unsigned char* ws = static_cast<unsigned char*>(job.workspace);
     ws = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+    SeedGrid* seed = reinterpret_cast<SeedGrid*>(ws);
+    double* bbox = reinterpret_cast<double*>(ws + 128);
+    int* sat = reinterpret_cast<int*>(ws + 512);
+    ws += SEED_BYTES;
     const size_t nslots = (size_t)slots * MAX_TQ;
     args.list_d = reinterpret_cast<double*>(ws);
     args.cand = reinterpret_cast<unsigned*>(ws + nslots * kp * sizeof(double));
     args.list_i = reinterpret_cast<int*>(ws + nslots * kp * sizeof(double) + nslots * CAP * sizeof(unsigned));
+    args.seed = seed;
+    args.sat = sat;
+
+    // ---- seed grid pre-pass: bbox -> geometry -> histogram -> summed-area table ----
+    const int pre_blocks = (int)((job.n + 255) / 256 < (long long)sms * 8 ? (job.n + 255) / 256 : (long long)sms * 8);
+    seed_init_kernel<<<1, 1, 0, stream>>>(bbox);
+    seed_bbox_kernel<<<pre_blocks, 256, 0, stream>>>(job.s_a, job.s_b, job.n, bbox);
+    seed_geometry_kernel<<<1, 1, 0, stream>>>(bbox, job.n, seed);
+    CMX_CUDA(cudaMemsetAsync(sat, 0, (size_t)SAT_LD * SAT_LD * sizeof(int), stream));
+    seed_hist_kernel<<<pre_blocks, 256, 0, stream>>>(job.s_a, job.s_b, job.n, seed, sat);
+    seed_rowscan_kernel<<<GMAX, 32, 0, stream>>>(seed, sat);
+    seed_colscan_kernel<<<(GMAX + 127) / 128, 128, 0, stream>>>(seed, sat);
+    for (int i = 0; i < 6; ++i) note_launch();
+    int rc = check_launch();
+    if (rc != CMX_OK) return rc;
 
     const int e = list_slots(job.k);
     if (big) {

@@ -54,25 +54,6 @@ __device__ __forceinline__ void tile_of_block(long long b, int& bi, int& bj) {
     bj = (int)(b - (long long)bi * (bi + 1) / 2);
 }
 
-__device__ __forceinline__ void atomic_min_double(double* addr, double v) {
-    unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
-    unsigned long long old = *a;
-    while (__longlong_as_double((long long)old) > v) {
-        const unsigned long long prev = atomicCAS(a, old, (unsigned long long)__double_as_longlong(v));
-        if (prev == old) break;
-        old = prev;
-    }
-}
-__device__ __forceinline__ void atomic_max_double(double* addr, double v) {
-    unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
-    unsigned long long old = *a;
-    while (__longlong_as_double((long long)old) < v) {
-        const unsigned long long prev = atomicCAS(a, old, (unsigned long long)__double_as_longlong(v));
-        if (prev == old) break;
-        old = prev;
-    }
-}
-
 __global__ void minmax_init_kernel(double* minmax) {
     minmax[0] = __longlong_as_double(0x7ff0000000000000LL);
     minmax[1] = -__longlong_as_double(0x7ff0000000000000LL);

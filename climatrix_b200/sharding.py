@@ -1,0 +1,169 @@
+"""Target sharding: one GPU, several GPUs in one process, or one process per GPU (NCCL).
+
+Targets are independent given the (replicated) samples, so the path shards by
+contiguous latitude-row bands of the dense target grid (or index ranges of a
+sparse target), SURVEY.md section 8e.  The only exchange step is the gather of
+the output slabs.
+
+* ``idw_on_devices``   -- host arrays in, host array out; used by the
+  reconstructor classes.  ``devices=[...]`` runs the bands concurrently on
+  several GPUs of this process.
+* ``distributed_idw`` / ``distributed_ok`` -- one process per GPU under
+  ``torchrun``: every rank computes its band with the CUDA kernels and the slabs
+  are all-gathered over NCCL (NVLink/NVSwitch).  The band computation is
+  injectable so that the partition/gather logic is testable on CPU with gloo.
+"""
+
+from __future__ import annotations
+
+from typing import Callable
+
+import numpy as np
+
+__all__ = ["row_shards", "idw_on_devices", "distributed_idw", "distributed_bands", "assemble_bands"]
+
+
+def row_shards(n_rows: int, parts: int) -> list[tuple[int, int]]:
+    """``parts`` contiguous [r0, r1) bands covering ``n_rows``; sizes differ by at most one."""
+    parts = max(1, int(parts))
+    base, extra = divmod(int(n_rows), parts)
+    out, r0 = [], 0
+    for p in range(parts):
+        r1 = r0 + base + (1 if p < extra else 0)
+        out.append((r0, r1))
+        r0 = r1
+    return out
+
+
+def idw_on_devices(s_lat, s_lon, values, t_lat, t_lon, grid: bool, *, k: int, power: float, k_min: int,
+                   dtype, device=None, devices=None, return_neighbours: bool = False):
+    """IDW with host (NumPy) inputs and output; H2D and D2H copies included.
+
+    values: (N,) or (T, N).  Returns (M,) or (T, M) as a NumPy array.
+    """
+    import torch
+
+    from . import kernels
+
+    if devices is None or len(devices) <= 1:
+        dev = kernels._require_cuda(devices[0] if devices else device)
+        with torch.cuda.device(dev):
+            targets = kernels.Targets.make(t_lat, t_lon, grid, dev)
+            res = kernels.idw(s_lat, s_lon, values, targets, k=k, power=power, k_min=k_min, dtype=dtype,
+                              return_neighbours=return_neighbours)
+            if return_neighbours:
+                out, dist, idx = res
+                return _to_host(out), _to_host(dist), _to_host(idx)
+            return _to_host(res)
+
+    # several GPUs driven from this process: launch every band, then collect
+    devs = [kernels._require_cuda(d) for d in devices]
+    n_rows = len(t_lat)
+    bands = row_shards(n_rows, len(devs))
+    pending = []
+    for dev, (r0, r1) in zip(devs, bands):
+        if r1 == r0:
+            continue
+        with torch.cuda.device(dev):
+            lat_band = t_lat[r0:r1]
+            lon_band = t_lon if grid else t_lon[r0:r1]
+            targets = kernels.Targets.make(lat_band, lon_band, grid, dev)
+            out = kernels.idw(s_lat, s_lon, values, targets, k=k, power=power, k_min=k_min, dtype=dtype)
+            pending.append(out)
+    parts = [_to_host(o) for o in pending]
+    return np.concatenate(parts, axis=-1)
+
+
+_pinned: dict = {}
+
+
+def _to_host(t):
+    """Device -> host through a cached pinned staging buffer (large results)."""
+    import torch
+
+    if t.numel() * t.element_size() < (1 << 22):
+        return t.cpu().numpy()
+    key = (t.dtype, t.device.index)
+    buf = _pinned.get(key)
+    if buf is None or buf.numel() < t.numel():
+        buf = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
+        _pinned[key] = buf
+    view = buf[: t.numel()].view(t.shape)
+    view.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return view.numpy().copy()
+
+
+# --------------------------------------------------------------------------- #
+# one process per GPU
+# --------------------------------------------------------------------------- #
+def assemble_bands(gathered, bands, n_batch: int, n_cols: int):
+    """[R][T][rows_max*n_cols] padded slabs -> [T][n_rows*n_cols] in the reference layout
+    (time, latitude, longitude), dataset/domain.py:1081-1098."""
+    import torch
+
+    pieces = []
+    for r, (r0, r1) in enumerate(bands):
+        rows = r1 - r0
+        if rows:
+            pieces.append(gathered[r].view(n_batch, -1)[:, : rows * n_cols])
+    return torch.cat(pieces, dim=1)
+
+
+def distributed_bands(compute: Callable, n_rows: int, n_cols: int, n_batch: int, *, dtype, device, group=None,
+                      gather: str = "all"):
+    """Run ``compute(r0, r1) -> tensor [n_batch, (r1-r0)*n_cols]`` on this rank's band and gather.
+
+    gather="all": every rank returns the full [n_batch, n_rows*n_cols] tensor (all-gather);
+    gather="none": returns only the local slab (the caller keeps the field sharded).
+    """
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    bands = row_shards(n_rows, world)
+    r0, r1 = bands[rank]
+    local = compute(r0, r1)
+    if local is None:
+        local = torch.empty((n_batch, 0), dtype=dtype, device=device)
+    local = local.reshape(n_batch, -1)
+    if gather == "none" or world == 1:
+        return local if gather == "none" else local
+    rows_max = max(b[1] - b[0] for b in bands)
+    padded = torch.zeros((n_batch, rows_max * n_cols), dtype=dtype, device=device)
+    padded[:, : local.shape[1]] = local
+    gathered = torch.empty((world, n_batch, rows_max * n_cols), dtype=dtype, device=device)
+    dist.all_gather_into_tensor(gathered.view(-1), padded.view(-1), group=group)
+    return assemble_bands(gathered, bands, n_batch, n_cols)
+
+
+def distributed_idw(s_lat, s_lon, values, t_lat, t_lon, grid: bool, *, k: int, power: float = 2.0, k_min: int = 2,
+                    dtype=None, layout=None, group=None, gather: str = "all", compute: Callable | None = None):
+    """IDW over all ranks of ``group``: samples replicated, target rows sharded, slabs gathered.
+
+    Inputs are device tensors (or NumPy, copied once per rank).  Returns [T, M] (or [M]
+    for a single slice) on this rank's device.
+    """
+    import torch
+
+    from . import kernels
+
+    dtype = dtype or torch.float64
+    dev = kernels._require_cuda() if compute is None else torch.device("cpu")
+    n_rows = len(t_lat)
+    n_cols = len(t_lon) if grid else 1
+    single = not (hasattr(values, "dim") and values.dim() == 2) and not (isinstance(values, np.ndarray) and values.ndim == 2)
+    n_batch = 1 if single else (values.shape[1] if layout == "sample_major" else values.shape[0])
+
+    if compute is None:
+        def compute(r0, r1):  # noqa: E306
+            if r1 == r0:
+                return None
+            lat_band = t_lat[r0:r1]
+            lon_band = t_lon if grid else t_lon[r0:r1]
+            targets = kernels.Targets.make(lat_band, lon_band, grid, dev)
+            return kernels.idw(s_lat, s_lon, values, targets, k=k, power=power, k_min=k_min, dtype=dtype, layout=layout)
+
+    out = distributed_bands(compute, n_rows, n_cols, n_batch, dtype=dtype, device=dev, group=group, gather=gather)
+    return out[0] if single else out
