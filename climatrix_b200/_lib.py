@@ -34,6 +34,10 @@ SIGNATURES = {
     "cmx_ok_workspace_bytes": (c_size_t, [c_int, c_i64]),
     "cmx_ok_mw_f64": (c_int, [_P, _P, _P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, c_int, c_int, ctypes.POINTER(c_double), c_int, c_double, c_double, _P, _P, _P, _P, c_size_t, _P]),
     "cmx_ok_mw_f32": (c_int, [_P, _P, _P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, c_int, c_int, ctypes.POINTER(c_double), c_int, c_double, c_double, _P, _P, _P, _P, c_size_t, _P]),
+    "cmx_timing_enable": (None, [c_int]),
+    "cmx_timing_reset": (None, []),
+    "cmx_timing_read": (c_int, [c_int, ctypes.POINTER(c_double), ctypes.POINTER(c_i64)]),
+    "cmx_fp32_peak_tflops": (c_double, []),
     "cmx_launch_count": (c_i64, []),
     "cmx_reset_launch_count": (None, []),
 }

@@ -22,6 +22,47 @@ int check_launch() {
     return e == cudaSuccess ? CMX_OK : cuda_fail(e);
 }
 
+// ---- optional per-kernel timing -------------------------------------------------------
+namespace {
+constexpr int kKinds = 3;
+constexpr int kMaxPairs = 256;
+struct TimingState {
+    bool on = false;
+    cudaEvent_t ev[kKinds][kMaxPairs][2];
+    int made[kKinds] = {0, 0, 0};
+    int used[kKinds] = {0, 0, 0};
+    long long dropped[kKinds] = {0, 0, 0};
+    bool open[kKinds] = {false, false, false};
+} g_timing;
+}  // namespace
+
+void timing_begin(int kind, cudaStream_t s) {
+    TimingState& t = g_timing;
+    if (!t.on || kind < 0 || kind >= kKinds) return;
+    if (t.used[kind] >= kMaxPairs) {
+        ++t.dropped[kind];
+        return;
+    }
+    const int i = t.used[kind];
+    if (i >= t.made[kind]) {
+        if (cudaEventCreate(&t.ev[kind][i][0]) != cudaSuccess || cudaEventCreate(&t.ev[kind][i][1]) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        t.made[kind] = i + 1;
+    }
+    cudaEventRecord(t.ev[kind][i][0], s);
+    t.open[kind] = true;
+}
+
+void timing_end(int kind, cudaStream_t s) {
+    TimingState& t = g_timing;
+    if (!t.on || kind < 0 || kind >= kKinds || !t.open[kind]) return;
+    cudaEventRecord(t.ev[kind][t.used[kind]][1], s);
+    ++t.used[kind];
+    t.open[kind] = false;
+}
+
 int sm_count() {
     static thread_local int cached_dev = -1, cached = 0;
     int dev = 0;
@@ -64,6 +105,71 @@ const char* cmx_last_cuda_error(void) { return cmx::g_cuda_err; }
 
 int64_t cmx_launch_count(void) { return cmx::g_launches; }
 void cmx_reset_launch_count(void) { cmx::g_launches = 0; }
+
+void cmx_timing_enable(int on) { cmx::g_timing.on = on != 0; }
+void cmx_timing_reset(void) {
+    for (int k = 0; k < cmx::kKinds; ++k) {
+        cmx::g_timing.used[k] = 0;
+        cmx::g_timing.dropped[k] = 0;
+        cmx::g_timing.open[k] = false;
+    }
+}
+int cmx_timing_read(int kind, double* total_ms, int64_t* launches) {
+    if (kind < 0 || kind >= cmx::kKinds || !total_ms || !launches) return CMX_ERR_BAD_ARG;
+    double sum = 0.0;
+    for (int i = 0; i < cmx::g_timing.used[kind]; ++i) {
+        float ms = 0.f;
+        CMX_CUDA(cudaEventSynchronize(cmx::g_timing.ev[kind][i][1]));
+        CMX_CUDA(cudaEventElapsedTime(&ms, cmx::g_timing.ev[kind][i][0], cmx::g_timing.ev[kind][i][1]));
+        sum += ms;
+    }
+    *total_ms = sum;
+    *launches = cmx::g_timing.used[kind];
+    return CMX_OK;
+}
+
+namespace cmx {
+namespace {
+__global__ void ffma_peak_kernel(float* out, float a, float b, int iters) {
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = threadIdx.x * 0.001f + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+}  // namespace cmx
+
+double cmx_fp32_peak_tflops(void) {
+    const int threads = 256, iters = 8192;
+    const int blocks = cmx::sm_count() * 8;
+    float* out = nullptr;
+    if (cudaMalloc(&out, (size_t)blocks * threads * sizeof(float)) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = -1.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        cmx::ffma_peak_kernel<<<blocks, threads>>>(out, 1.0001f, 0.5f, iters);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = (double)blocks * threads * iters * 16 * 2 / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;  // first launch warms up
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return best;
+}
 
 size_t cmx_knn_workspace_bytes(int k) { return cmx::knn_workspace_bytes(k); }
 

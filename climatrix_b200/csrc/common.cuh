@@ -16,6 +16,8 @@ void note_launch();                 // ++launch counter
 int cuda_fail(cudaError_t e);       // records text, returns CMX_ERR_CUDA
 int check_launch();                 // cudaGetLastError() -> CMX_OK / CMX_ERR_CUDA
 int sm_count();                     // SMs of the current device (cached)
+void timing_begin(int kind, cudaStream_t s);  // no-ops unless cmx_timing_enable(1)
+void timing_end(int kind, cudaStream_t s);
 
 #define CMX_CUDA(call)                                   \
     do {                                                 \

@@ -187,9 +187,11 @@ int idw_from_table(const int* idx, const double* dd, int dist_is_squared, long l
     const long long blocks = (M + BW_TARGETS - 1) / BW_TARGETS;
     if (smem > 48 * 1024)
         CMX_CUDA(cudaFuncSetAttribute(idw_batch_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    timing_begin(CMX_KERNEL_IDW_BATCH, stream);
     idw_batch_kernel<V><<<(unsigned)blocks, BW_THREADS, smem, stream>>>(idx, dd, dist_is_squared, M, k_table, k_use,
                                                                        k_min, power, vals, n_batch, stride_t,
                                                                        stride_i, flag_scratch, out);
+    timing_end(CMX_KERNEL_IDW_BATCH, stream);
     note_launch();
     return check_launch();
 }

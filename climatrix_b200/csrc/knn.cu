@@ -428,7 +428,10 @@ __device__ __forceinline__ float min3f(float a, float b, float c) {
     return d;
 }
 
-template <int E, int QPT>
+// COLSHARE: dense-grid targets -- the QPT targets of a thread sit in one grid column, so the
+// column term  u = |s|^2 - 2 q_b s_b  is evaluated once per sample and thread and each pair
+// costs a single FMA (t = u - 2 q_a s_a).  Explicit target points use the generic two-FMA form.
+template <int E, int QPT, bool COLSHARE>
 __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __grid_constant__ KnnArgs a) {
     constexpr int TQ = WARPS * QPT * 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -466,7 +469,7 @@ __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __g
             for (int q = 0; q < QPT; ++q) {
                 long long m;
                 ta[q] = 0.0;
-                tb[q] = 0.0;
+                tb[q] = q ? tb[0] : 0.0;  // COLSHARE: rows beyond the grid inherit the column coordinate
                 if (target_coords<QPT>(a, tile, (warp * QPT + q) * 32 + lane, ta[q], tb[q], m)) {
                     validm |= 1u << q;
                     mn_a = fmin(mn_a, ta[q]);
@@ -501,7 +504,7 @@ __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __g
                 const float qa = __double2float_rn(__dsub_rn(ta[q], ca));
                 const float qb = __double2float_rn(__dsub_rn(tb[q], cb));
                 Qa[q] = ok ? -2.0f * qa : 0.0f;
-                Qb[q] = ok ? -2.0f * qb : 0.0f;
+                Qb[q] = (ok || COLSHARE) ? -2.0f * qb : 0.0f;
                 // rigorous starting threshold from the sample-count grid (never below the true k-th distance)
                 thr[q] = ok ? filter_threshold(seed_bound_d2(seed, a.sat, ta[q], tb[q], a.j.k), qa, qb) : -CMX_INF_F;
                 off[q] = 0;
@@ -575,14 +578,27 @@ __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __g
                     const float4 A4 = *reinterpret_cast<const float4*>(cA + g0 + j);
                     const float4 B4 = *reinterpret_cast<const float4*>(cB + g0 + j);
                     const float4 S4 = *reinterpret_cast<const float4*>(cS + g0 + j);
+                    if (COLSHARE) {
+                        float u0, u1, u2, u3;
+                        fma2_bcast(Qb[0], B4.x, B4.y, S4.x, S4.y, u0, u1);
+                        fma2_bcast(Qb[0], B4.z, B4.w, S4.z, S4.w, u2, u3);
 #pragma unroll
-                    for (int q = 0; q < QPT; ++q) {
-                        float u0, u1, u2, u3, t0, t1, t2, t3;
-                        fma2_bcast(Qb[q], B4.x, B4.y, S4.x, S4.y, u0, u1);
-                        fma2_bcast(Qb[q], B4.z, B4.w, S4.z, S4.w, u2, u3);
-                        fma2_bcast(Qa[q], A4.x, A4.y, u0, u1, t0, t1);
-                        fma2_bcast(Qa[q], A4.z, A4.w, u2, u3, t2, t3);
-                        mn[q] = min3f(min3f(mn[q], t0, t1), t2, t3);
+                        for (int q = 0; q < QPT; ++q) {
+                            float t0, t1, t2, t3;
+                            fma2_bcast(Qa[q], A4.x, A4.y, u0, u1, t0, t1);
+                            fma2_bcast(Qa[q], A4.z, A4.w, u2, u3, t2, t3);
+                            mn[q] = min3f(min3f(mn[q], t0, t1), t2, t3);
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < QPT; ++q) {
+                            float u0, u1, u2, u3, t0, t1, t2, t3;
+                            fma2_bcast(Qb[q], B4.x, B4.y, S4.x, S4.y, u0, u1);
+                            fma2_bcast(Qb[q], B4.z, B4.w, S4.z, S4.w, u2, u3);
+                            fma2_bcast(Qa[q], A4.x, A4.y, u0, u1, t0, t1);
+                            fma2_bcast(Qa[q], A4.z, A4.w, u2, u3, t2, t3);
+                            mn[q] = min3f(min3f(mn[q], t0, t1), t2, t3);
+                        }
                     }
                 }
                 // ---- groups that may hold a neighbour: the warp re-examines them, one sample per lane ----
@@ -662,8 +678,15 @@ __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __g
 template <int E, int QPT>
 int launch(const KnnArgs& args, int ctas, cudaStream_t stream) {
     const size_t smem = 2 * TS * sizeof(double) + 6 * TS * sizeof(float);
-    CMX_CUDA(cudaFuncSetAttribute(knn_kernel<E, QPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knn_kernel<E, QPT><<<ctas, THREADS, smem, stream>>>(args);
+    timing_begin(CMX_KERNEL_KNN, stream);
+    if (args.j.grid) {
+        CMX_CUDA(cudaFuncSetAttribute(knn_kernel<E, QPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_kernel<E, QPT, true><<<ctas, THREADS, smem, stream>>>(args);
+    } else {
+        CMX_CUDA(cudaFuncSetAttribute(knn_kernel<E, QPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_kernel<E, QPT, false><<<ctas, THREADS, smem, stream>>>(args);
+    }
+    timing_end(CMX_KERNEL_KNN, stream);
     note_launch();
     return check_launch();
 }

@@ -227,7 +227,9 @@ int launch_ok(const OkArgs& a, cudaStream_t stream) {
     long long ctas = (a.M + warps - 1) / warps;
     const long long cap = (long long)sm_count() * 8;
     if (ctas > cap) ctas = cap;
+    timing_begin(CMX_KERNEL_OK_SOLVE, stream);
     ok_solve_kernel<E, V><<<(unsigned)ctas, warps * 32, smem, stream>>>(a, warps);
+    timing_end(CMX_KERNEL_OK_SOLVE, stream);
     note_launch();
     return check_launch();
 }

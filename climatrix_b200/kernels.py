@@ -116,6 +116,30 @@ def reset_launch_count() -> None:
     _lib.load().cmx_reset_launch_count()
 
 
+KERNEL_KNN, KERNEL_IDW_BATCH, KERNEL_OK_SOLVE = 0, 1, 2
+
+
+def kernel_timing(enable: bool) -> None:
+    """Bracket the hot kernels with CUDA events on their stream (bench.py's roofline)."""
+    lib = _lib.load()
+    lib.cmx_timing_enable(int(bool(enable)))
+    lib.cmx_timing_reset()
+
+
+def kernel_time(kind: int):
+    """(total milliseconds, launches) of one kernel kind since ``kernel_timing(True)`` / the last read."""
+    lib = _lib.load()
+    ms, n = ctypes.c_double(0.0), ctypes.c_int64(0)
+    _lib.check(lib.cmx_timing_read(kind, ctypes.byref(ms), ctypes.byref(n)), "cmx_timing_read")
+    lib.cmx_timing_reset()
+    return ms.value, n.value
+
+
+def fp32_peak_tflops() -> float:
+    _require_cuda()
+    return float(_lib.load().cmx_fp32_peak_tflops())
+
+
 def _check_samples(s_lat, s_lon):
     if s_lat.dim() != 1 or s_lat.shape != s_lon.shape:
         raise ValueError(

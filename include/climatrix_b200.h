@@ -181,6 +181,24 @@ size_t cmx_ok_workspace_bytes(int k, int64_t n_targets);
 int64_t cmx_launch_count(void);
 void cmx_reset_launch_count(void);
 
+/*
+ * Optional per-kernel device timing (bench.py's roofline): when enabled, the library brackets
+ * its two hot kernels with CUDA events on the launching stream.
+ *   kind 0 = K1 neighbour search (knn_kernel), kind 1 = K2 batched IDW apply, kind 2 = K4 kriging solve.
+ * cmx_timing_read synchronises on the recorded events and returns the accumulated
+ * milliseconds and the number of launches since the last cmx_timing_reset.
+ */
+#define CMX_KERNEL_KNN 0
+#define CMX_KERNEL_IDW_BATCH 1
+#define CMX_KERNEL_OK_SOLVE 2
+void cmx_timing_enable(int on);
+void cmx_timing_reset(void);
+int cmx_timing_read(int kind, double* total_ms, int64_t* launches);
+
+/* FP32 FFMA throughput of the current device, measured now (TFLOP/s, 2 flop per FMA);
+ * the denominator of the K1 roofline.  Synchronous; < 0 on error. */
+double cmx_fp32_peak_tflops(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,78 @@
+"""CPU: libclimatrix_b200.so loads and exports every symbol include/climatrix_b200.h declares.
+
+No compute call is made here (there is no GPU in the build container); only entry points
+that return before touching the device are exercised.
+"""
+
+import ctypes
+import os
+
+import pytest
+
+from climatrix_b200 import _lib
+from climatrix_b200.build import LIB_PATH, build
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(LIB_PATH):
+        build()
+    return _lib.load()
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    declared = _lib.header_symbols()
+    assert len(declared) >= 17
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but missing from the library"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(declared)
+
+
+def test_version_and_error_strings(lib):
+    assert lib.cmx_version() >= 100
+    assert lib.cmx_strerror(0) == b"ok"
+    assert b"exceeds the number of samples" in lib.cmx_strerror(_lib.ERR_K_GT_N)
+    assert lib.cmx_strerror(-99) == b"unknown error"
+
+
+def test_workspace_queries(lib):
+    assert lib.cmx_knn_workspace_bytes(0) == 0
+    assert lib.cmx_knn_workspace_bytes(_lib.MAX_K + 1) == 0
+    w32, w64, w128 = (lib.cmx_knn_workspace_bytes(k) for k in (32, 64, 128))
+    assert 0 < w32 < w64 < w128
+    assert lib.cmx_idw_workspace_bytes(32, 1000, 1) == 0
+    assert lib.cmx_idw_workspace_bytes(32, 1000, 4) >= 1000 * 32 * 12
+    assert lib.cmx_ok_workspace_bytes(32, 1000) > w32
+
+
+def test_argument_validation_returns_codes_without_a_device(lib):
+    null = ctypes.c_void_p(None)
+    one = ctypes.c_void_p(16)  # never dereferenced: validation fails first
+    # null pointers
+    assert lib.cmx_knn(null, null, 10, null, 1, null, 1, 1, 3, null, null, null, 0, null) == _lib.ERR_BAD_ARG
+    # k > n
+    assert lib.cmx_knn(one, one, 2, one, 1, one, 1, 1, 3, one, null, one, 1 << 40, null) == _lib.ERR_K_GT_N
+    # k above CMX_MAX_K
+    assert lib.cmx_knn(one, one, 1000, one, 1, one, 1, 1, 129, one, null, one, 1 << 40, null) == _lib.ERR_K_TOO_LARGE
+    # workspace too small
+    assert lib.cmx_knn(one, one, 1000, one, 4, one, 4, 1, 8, one, null, one, 16, null) == _lib.ERR_WORKSPACE
+    # sparse targets need matching lengths
+    assert lib.cmx_knn(one, one, 1000, one, 4, one, 5, 0, 8, one, null, one, 1 << 40, null) == _lib.ERR_BAD_ARG
+    # variogram: too many lags / unknown metric
+    assert lib.cmx_variogram_bins(one, one, one, 10, 0, 65, one, one, one, one, null) == _lib.ERR_UNSUPPORTED
+    assert lib.cmx_variogram_minmax(one, one, 10, 7, one, null) == _lib.ERR_UNSUPPORTED
+    p = (ctypes.c_double * 3)(1.0, 1.0, 0.0)
+    assert lib.cmx_ok_mw_f64(one, one, one, 10, one, 2, one, 2, 1, 0, 4, 9, p, 1, 1.0, 0.0, one, null, null, one, 1 << 40, null) == _lib.ERR_UNSUPPORTED
+
+
+def test_check_maps_codes_to_python_exceptions():
+    with pytest.raises(IndexError):
+        _lib.check(_lib.ERR_K_GT_N, "x")  # the reference fails with IndexError too (idw.py:167)
+    with pytest.raises(ValueError):
+        _lib.check(_lib.ERR_BAD_ARG, "x")
+    with pytest.raises(NotImplementedError):
+        _lib.check(_lib.ERR_UNSUPPORTED, "x")
+    with pytest.raises(RuntimeError):
+        _lib.check(_lib.ERR_CUDA, "x")
+    _lib.check(0)

@@ -1,0 +1,407 @@
+"""GPU (-m gpu): the CUDA path against the CPU oracle and the reference-generated golden vectors.
+
+Everything goes through the public API (reconstructor classes or climatrix_b200.kernels),
+i.e. through the C ABI of libclimatrix_b200.so.  Tolerances (BASELINE.json north_star):
+neighbour sets bit-exact, IDW fields 1e-5 relative, kriging fields 1e-4 relative.
+"""
+
+import warnings
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import torch  # noqa: E402
+
+import climatrix_b200 as cm  # noqa: E402
+from climatrix_b200 import kernels as K  # noqa: E402
+from conftest import golden_names, load_golden  # noqa: E402
+from helpers import dense_dataset, rel_err, sparse_dataset, static_sparse, synthetic_field  # noqa: E402
+from oracle import pykrige_restated as pk  # noqa: E402
+from oracle.idw_oracle import (  # noqa: E402
+    dense_points, idw_oracle, idw_oracle_batched, knn_bruteforce, knn_ckdtree, sparse_points,
+)
+from oracle.ok_oracle import ok_oracle  # noqa: E402
+
+IDW_RTOL = 1e-5
+OK_RTOL = 1e-4
+DEV = "cuda:0"
+
+
+def _samples(n, seed, lat=(-90, 90), lon=(-180, 180)):
+    rng = np.random.default_rng(seed)
+    la, lo = rng.uniform(*lat, n), rng.uniform(*lon, n)
+    return la, lo, synthetic_field(la, lo, rng), rng
+
+
+# ------------------------------------------------------------------------------------------
+# K1: neighbour search == scipy cKDTree, bit for bit
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize(
+    "n,n_lat,n_lon,k",
+    [(1000, 180, 360, 30), (5000, 45, 90, 32), (300, 17, 35, 5), (3000, 60, 70, 64), (700, 33, 31, 100),
+     (40, 9, 18, 1), (5000, 7, 9, 8), (2049, 40, 40, 33), (4096, 3, 1000, 16), (128, 50, 50, 128)],
+)
+def test_knn_grid_matches_ckdtree(n, n_lat, n_lon, k):
+    la, lo, _, _ = _samples(n, n + k)
+    tl, to = np.linspace(-89.5, 89.5, n_lat), np.linspace(-179.5, 179.5, n_lon)
+    dist, idx = K.knn(la, lo, K.Targets.make(tl, to, True, DEV), k)
+    d0, i0 = knn_ckdtree(sparse_points(la, lo), dense_points(tl, to), k)
+    np.testing.assert_array_equal(idx.cpu().numpy(), i0)
+    np.testing.assert_array_equal(dist.cpu().numpy(), d0)  # sqrt(dx*dx+dy*dy), no FMA: bit-equal
+
+
+def test_knn_sparse_targets_and_descending_axes():
+    la, lo, _, rng = _samples(4000, 11)
+    tl, to = rng.uniform(-90, 90, 5000), rng.uniform(-180, 180, 5000)
+    dist, idx = K.knn(la, lo, K.Targets.make(tl, to, False, DEV), 16)
+    d0, i0 = knn_ckdtree(sparse_points(la, lo), sparse_points(tl, to), 16)
+    np.testing.assert_array_equal(idx.cpu().numpy(), i0)
+    np.testing.assert_array_equal(dist.cpu().numpy(), d0)
+    # ERA5-style axes: latitude 90 -> -90, longitude 0..360
+    lo360 = lo % 360
+    tl, to = np.linspace(90, -90, 91), np.arange(0, 360, 2.5)
+    dist, idx = K.knn(la, lo360, K.Targets.make(tl, to, True, DEV), 12)
+    d0, i0 = knn_ckdtree(sparse_points(la, lo360), dense_points(tl, to), 12)
+    np.testing.assert_array_equal(idx.cpu().numpy(), i0)
+    np.testing.assert_array_equal(dist.cpu().numpy(), d0)
+
+
+def test_knn_clustered_samples_small_distances():
+    """Distances ~1e-3 deg next to coordinates ~50: the fp32 filter margin must not lose anyone."""
+    rng = np.random.default_rng(12)
+    la, lo = 50 + rng.normal(scale=0.05, size=20000), 10 + rng.normal(scale=0.05, size=20000)
+    tl, to = np.linspace(49.8, 50.2, 101), np.linspace(9.8, 10.2, 101)
+    dist, idx = K.knn(la, lo, K.Targets.make(tl, to, True, DEV), 32)
+    d0, i0 = knn_ckdtree(sparse_points(la, lo), dense_points(tl, to), 32)
+    np.testing.assert_array_equal(idx.cpu().numpy(), i0)
+    np.testing.assert_array_equal(dist.cpu().numpy(), d0)
+
+
+def test_knn_far_away_targets_and_two_scales():
+    """Targets well outside the sample bounding box, and a mix of a dense cluster and a sparse halo."""
+    rng = np.random.default_rng(13)
+    la = np.concatenate([rng.normal(0, 0.01, 3000), rng.uniform(-80, 80, 300)])
+    lo = np.concatenate([rng.normal(0, 0.01, 3000), rng.uniform(-170, 170, 300)])
+    tl, to = np.linspace(-85, 85, 35), np.linspace(-175, 175, 36)
+    dist, idx = K.knn(la, lo, K.Targets.make(tl, to, True, DEV), 20)
+    d0, i0 = knn_ckdtree(sparse_points(la, lo), dense_points(tl, to), 20)
+    np.testing.assert_array_equal(idx.cpu().numpy(), i0)
+    tl, to = np.linspace(200, 300, 11), np.linspace(400, 500, 13)  # nowhere near the samples
+    dist, idx = K.knn(la, lo, K.Targets.make(tl, to, True, DEV), 7)
+    d0, i0 = knn_ckdtree(sparse_points(la, lo), dense_points(tl, to), 7)
+    np.testing.assert_array_equal(idx.cpu().numpy(), i0)
+    np.testing.assert_array_equal(dist.cpu().numpy(), d0)
+
+
+def test_knn_ties_follow_the_documented_rule():
+    """Lattice samples: exact distance ties.  cKDTree's choice is traversal dependent;
+    ours is (squared distance, index).  Distances must still agree with cKDTree exactly."""
+    gl, go = np.meshgrid(np.arange(-20.0, 21), np.arange(-20.0, 21), indexing="ij")
+    la, lo = gl.ravel(), go.ravel()
+    tl = to = np.arange(-10.0, 11, 0.5)
+    dist, idx = K.knn(la, lo, K.Targets.make(tl, to, True, DEV), 9)
+    d1, i1 = knn_bruteforce(sparse_points(la, lo), dense_points(tl, to), 9)
+    np.testing.assert_array_equal(idx.cpu().numpy(), i1)
+    d0, i0 = knn_ckdtree(sparse_points(la, lo), dense_points(tl, to), 9)
+    np.testing.assert_array_equal(dist.cpu().numpy(), d0)  # tie-aware: same distance multiset per target
+    differs = (np.sort(idx.cpu().numpy(), 1) != np.sort(i0, 1)).any(1)
+    kth = d0[:, -1]
+    for m in np.nonzero(differs)[0][:50]:  # any differing index sits exactly at the k-th distance
+        ours, theirs = set(idx[m].tolist()), set(i0[m].tolist())
+        for j in ours ^ theirs:
+            assert np.hypot(dense_points(tl, to)[m, 0] - la[j], dense_points(tl, to)[m, 1] - lo[j]) == kth[m]
+
+
+def test_knn_duplicate_coordinates_and_k_errors():
+    la, lo, _, _ = _samples(150, 3)
+    la[100:], lo[100:] = la[:50], lo[:50]
+    tl, to = np.linspace(-85.3, 85.3, 21), np.linspace(-175.3, 175.3, 43)
+    dist, idx = K.knn(la, lo, K.Targets.make(tl, to, True, DEV), 7)
+    d1, i1 = knn_bruteforce(sparse_points(la, lo), dense_points(tl, to), 7)
+    np.testing.assert_array_equal(idx.cpu().numpy(), i1)
+    np.testing.assert_array_equal(dist.cpu().numpy(), d1)
+    with pytest.raises(IndexError):  # the reference dies with IndexError at idw.py:167 when k > N
+        K.knn(la[:5], lo[:5], K.Targets.make(tl, to, True, DEV), 6)
+    with pytest.raises(ValueError):
+        K.knn(la, lo, K.Targets.make(tl, to, True, DEV), 129)
+
+
+# ------------------------------------------------------------------------------------------
+# IDW through the reconstructor API, against reference-generated golden vectors
+# ------------------------------------------------------------------------------------------
+def _dataset_for(g):
+    m = g["meta"]
+    if m["source_sparse"]:
+        src = sparse_dataset(g["sample_lat"], g["sample_lon"], np.asarray(g["values"]).reshape(-1, 1))
+    else:
+        src = dense_dataset(g["sample_lat"], g["sample_lon"], g["values"])
+    tgt = cm.Domain.from_lat_lon(g["target_lat"], g["target_lon"], kind="sparse" if m["target_sparse"] else "dense")
+    return src, tgt
+
+
+@pytest.mark.parametrize("name", golden_names("idw_"))
+def test_idw_reconstructor_matches_reference_golden(name):
+    g = load_golden(name)
+    src, tgt = _dataset_for(g)
+    out = src.reconstruct(tgt, method="idw", **g["meta"]["kwargs"])
+    assert isinstance(out, cm.BaseClimatrixDataset)
+    assert out.domain.is_sparse == g["meta"]["target_sparse"]
+    got = np.asarray(out.da.values)
+    assert got.shape == g["expected"].shape and got.dtype == np.float64
+    # Tie-aware comparison (SURVEY.md section 7 "Ties"): where the k-th and (k+1)-th neighbour are
+    # exactly equidistant the reference's choice depends on kd-tree traversal order, ours on the sample
+    # index; such targets are well defined in neither and are excluded (duplicate-coordinate fixture).
+    k = g["meta"]["kwargs"].get("k", 5)
+    pts = sparse_points(g["sample_lat"], g["sample_lon"]) if g["meta"]["source_sparse"] else dense_points(g["sample_lat"], g["sample_lon"])
+    tq = tgt.get_all_spatial_points()
+    keep = np.ones(tq.shape[0], dtype=bool)
+    if k < pts.shape[0]:
+        d, _ = knn_bruteforce(pts, tq, k + 1)
+        keep = d[:, k] != d[:, k - 1]
+    assert keep.mean() > 0.5
+    if "duplicate" not in name:
+        assert keep.all(), "only the duplicate-coordinate fixture is expected to contain boundary ties"
+    assert rel_err(got.reshape(-1)[keep], g["expected"].reshape(-1)[keep]) <= IDW_RTOL
+
+
+@pytest.mark.parametrize("dtype,rtol", [("float64", 1e-12), ("float32", IDW_RTOL)])
+def test_idw_config1_full_size_vs_oracle(dtype, rtol):
+    """BASELINE config 1: 1000 samples -> 180x360, k=30, power=2."""
+    la, lo, v, _ = _samples(1000, 1234)
+    if dtype == "float32":
+        v = v.astype(np.float32).astype(np.float64)  # both sides see the same rounded values
+    tl, to = np.arange(-89.5, 90, 1.0), np.arange(-179.5, 180, 1.0)
+    src = static_sparse(la, lo, v)
+    out = cm.IDWReconstructor(src, cm.Domain.from_lat_lon(tl, to), k=30, power=2.0, k_min=2, dtype=dtype).reconstruct()
+    ref = idw_oracle(sparse_points(la, lo), v, dense_points(tl, to), k=30, power=2.0, k_min=2).reshape(180, 360)
+    assert out.da.values.dtype == np.dtype(dtype)
+    assert rel_err(out.da.values, ref) <= rtol
+
+
+@pytest.mark.parametrize("power,k,k_min", [(2.0, 8, 1), (0.5, 8, 4), (5.0, 8, 8), (1e-10, 12, 2), (-1.5, 6, 2), (3.3, 70, 40)])
+def test_idw_nonfinite_values_powers_kmin(power, k, k_min):
+    la, lo, v, rng = _samples(1500, 77)
+    bad = rng.choice(1500, 400, replace=False)
+    v[bad[:300]] = np.nan
+    v[bad[300:350]] = np.inf
+    v[bad[350:]] = -np.inf
+    tl, to = np.linspace(-88, 88, 45), np.linspace(-178, 178, 90)
+    out = K.idw(la, lo, v, K.Targets.make(tl, to, True, DEV), k=k, power=power, k_min=k_min).cpu().numpy()
+    with np.errstate(invalid="ignore"):
+        ref = idw_oracle(sparse_points(la, lo), v, dense_points(tl, to), k=k, power=power, k_min=k_min)
+    assert np.isnan(ref).sum() > 0 or k_min == 1
+    assert rel_err(out, ref) <= IDW_RTOL
+
+
+def test_idw_exact_hit_uses_the_distance_clamp():
+    la, lo, v, rng = _samples(500, 21)
+    tl, to = np.concatenate([la[:100], rng.uniform(-90, 90, 100)]), np.concatenate([lo[:100], rng.uniform(-180, 180, 100)])
+    out = K.idw(la, lo, v, K.Targets.make(tl, to, False, DEV), k=6).cpu().numpy()
+    ref = idw_oracle(sparse_points(la, lo), v, sparse_points(tl, to), k=6)
+    assert rel_err(out, ref) <= IDW_RTOL
+    np.testing.assert_allclose(out[:100], v[:100], rtol=1e-12)  # weight 1e20 on the coincident sample
+
+
+@pytest.mark.parametrize("layout", ["batch_major", "sample_major"])
+@pytest.mark.parametrize("dtype,rtol", [(torch.float64, 1e-12), (torch.float32, IDW_RTOL)])
+def test_idw_batched_equals_loop_of_static_calls(layout, dtype, rtol):
+    la, lo, _, rng = _samples(2000, 8)
+    t = 37
+    vt = np.stack([synthetic_field(la, lo, rng, phase=0.1 * i) for i in range(t)])
+    vt[3, rng.choice(2000, 100, replace=False)] = np.nan
+    vt[20, rng.choice(2000, 1500, replace=False)] = np.inf
+    if dtype == torch.float32:
+        vt = vt.astype(np.float32).astype(np.float64)
+    tl, to = np.linspace(-89, 89, 90), np.linspace(-179, 179, 179)
+    arr = vt if layout == "batch_major" else np.ascontiguousarray(vt.T)
+    out = K.idw(la, lo, arr, K.Targets.make(tl, to, True, DEV), k=32, power=2.0, k_min=2, layout=layout, dtype=dtype)
+    assert out.shape == (t, 90 * 179)
+    with np.errstate(invalid="ignore"):
+        ref = idw_oracle_batched(sparse_points(la, lo), vt, dense_points(tl, to), k=32)
+    assert rel_err(out.cpu().numpy(), ref) <= rtol
+
+
+def test_idw_dynamic_dataset_through_the_reconstructor():
+    """time x point source -> (time, lat, lon) result; each slice equals the static reference call."""
+    la, lo, _, rng = _samples(800, 9)
+    times = np.arange("2000-01-01", "2000-01-06", dtype="datetime64[D]").astype("datetime64[ns]")
+    vals = np.stack([synthetic_field(la, lo, rng, 0.3 * i) for i in range(len(times))], axis=1)  # (point, time)
+    src = sparse_dataset(la, lo, vals, times=times, name="t2m")
+    tgt = cm.Domain.from_lat_lon(np.linspace(-60, 60, 25), np.linspace(-120, 120, 49))
+    out = src.reconstruct(tgt, method="idw", k=10)
+    assert tuple(out.da.dims) == ("time", "lat", "lon") and out.da.values.shape == (5, 25, 49) and out.da.name == "t2m"
+    for i in range(len(times)):
+        ref = idw_oracle(sparse_points(la, lo), vals[:, i], tgt.get_all_spatial_points(), k=10).reshape(25, 49)
+        assert rel_err(out.da.values[i], ref) <= 1e-12
+    assert out.domain.is_dynamic
+
+
+def test_idw_apply_reuses_a_neighbour_table():
+    la, lo, v, _ = _samples(3000, 31)
+    tl, to = np.linspace(-80, 80, 41), np.linspace(-170, 170, 83)
+    T = K.Targets.make(tl, to, True, DEV)
+    _, dist, idx = K.idw(la, lo, v, T, k=50, return_neighbours=True)
+    for k, p, kmin in [(50, 2.0, 2), (12, 3.0, 1), (1, 0.7, 1), (27, 2.87, 2)]:
+        out = K.idw_apply(idx, dist, v, k=k, power=p, k_min=kmin).cpu().numpy()
+        ref = idw_oracle(sparse_points(la, lo), v, dense_points(tl, to), k=k, power=p, k_min=kmin)
+        assert rel_err(out, ref) <= 1e-12
+
+
+def test_reference_interface_combinations_return_the_right_kind():
+    """The four sparse/dense x sparse/dense cases of test_base_interface.py:235-279 (k=5 == N)."""
+    sp, de = sparse_dataset(), dense_dataset()
+    for src, tgt in [(de, sp.domain), (sp, de.domain), (de, de.domain), (sp, sp.domain)]:
+        out = cm.IDWReconstructor(src, tgt).reconstruct()
+        assert isinstance(out, cm.BaseClimatrixDataset) and out.domain.is_sparse == tgt.is_sparse
+        assert np.isfinite(np.asarray(out.da.values)).all()
+
+
+# ------------------------------------------------------------------------------------------
+# size-independent properties at a BASELINE-scale problem
+# ------------------------------------------------------------------------------------------
+def test_idw_properties_at_era5_scale():
+    """100 000 samples -> 721x1440 (config 3, one slice): partition of unity, bounds, sortedness,
+    determinism, and spot rows against the oracle."""
+    la, lo, v, _ = _samples(100_000, 1237, lon=(0, 360))
+    tl, to = np.linspace(90, -90, 721), np.arange(0, 360, 0.25)
+    T = K.Targets.make(tl, to, True, DEV)
+    s_la, s_lo = torch.as_tensor(la).to(DEV), torch.as_tensor(lo).to(DEV)
+    out, dist, idx = K.idw(s_la, s_lo, v, T, k=32, return_neighbours=True)
+    const = K.idw(s_la, s_lo, np.full_like(v, 7.25), T, k=32)
+    assert torch.allclose(const, torch.full_like(const, 7.25), rtol=1e-13, atol=0)          # weights sum to one
+    assert float(out.min()) >= v.min() - 1e-9 and float(out.max()) <= v.max() + 1e-9           # convex combination
+    assert bool((dist[:, 1:] >= dist[:, :-1]).all())                                           # ascending rows
+    srt = idx.sort(dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())                                             # no duplicates
+    out2 = K.idw(s_la, s_lo, v, T, k=32)
+    assert torch.equal(out, out2)                                                              # deterministic
+    lin = K.idw(s_la, s_lo, 3.0 * v - 2.0, T, k=32)
+    assert torch.allclose(lin, 3.0 * out - 2.0, rtol=1e-12, atol=1e-12)                        # linear in the values
+    rows = np.array([0, 1, 359, 360, 719, 720])
+    ref, d0, i0 = idw_oracle(sparse_points(la, lo), v, dense_points(tl[rows], to), k=32, return_neighbours=True)
+    sel = (rows[:, None] * 1440 + np.arange(1440)[None, :]).ravel()
+    np.testing.assert_array_equal(idx.cpu().numpy()[sel], i0)
+    np.testing.assert_array_equal(dist.cpu().numpy()[sel], d0)
+    assert rel_err(out.cpu().numpy()[sel], ref) <= 1e-12
+
+
+# ------------------------------------------------------------------------------------------
+# K3 / K4: variogram and moving-window kriging
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,nlags,geo", [(3000, 6, False), (777, 20, False), (257, 4, False), (800, 8, True)])
+def test_empirical_variogram_matches_restated_pykrige(n, nlags, geo):
+    rng = np.random.default_rng(n)
+    x, y, z = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n) * (1e-6 if n == 257 else 1.0), rng.normal(size=n)
+    lags, sv, raw = K.empirical_variogram(x, y, z, nlags, geographic=geo)
+    l0, s0, r0 = pk.empirical_variogram(np.stack([x, y], 1), z, nlags, "geographic" if geo else "euclidean")
+    np.testing.assert_array_equal(raw["count"], r0["count"])
+    if not geo:
+        assert raw["dmin"] == r0["dmin"] and raw["dmax"] == r0["dmax"]
+    np.testing.assert_allclose(lags, l0, rtol=1e-10)
+    np.testing.assert_allclose(sv, s0, rtol=1e-10)
+
+
+@pytest.mark.parametrize("model,k", [("spherical", 32), ("linear", 16), ("power", 12), ("exponential", 64), ("gaussian", 8), ("spherical", 100), ("linear", 1)])
+def test_moving_window_kernel_matches_restated_pykrige(model, k):
+    rng = np.random.default_rng(5 + k)
+    n = 1500
+    x, y = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    z = np.sin(3 * x) + np.cos(2 * y) + 0.1 * rng.normal(size=n)
+    okr = pk.OrdinaryKriging(x, y, z, variogram_model=model, nlags=6, anisotropy_scaling=1.0)
+    tx, ty = np.linspace(-1, 1, 40), np.linspace(-1, 1, 30)
+    zr, sr = okr.execute("grid", tx, ty, backend="loop", n_closest_points=k)
+    out, sig, nsing = K.ok_moving_window(okr.X_ADJUSTED, okr.Y_ADJUSTED, okr.Z, tx, ty, True, k=k, variogram_model=model,
+                                         params=okr.variogram_model_parameters, return_sigmasq=True)
+    assert int(nsing) == 0
+    scale = np.max(np.abs(zr))
+    assert np.max(np.abs(out.cpu().numpy().reshape(30, 40) - zr)) <= OK_RTOL * scale
+    assert np.max(np.abs(sig.cpu().numpy().reshape(30, 40) - sr)) <= OK_RTOL * max(np.max(np.abs(sr)), 1e-30)
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names("ok_mw_") if "geographic" not in n])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_ok_reconstructor_moving_window_matches_golden(name, dtype):
+    g = load_golden(name)
+    src = sparse_dataset(g["sample_lat"], g["sample_lon"], np.asarray(g["values"]).reshape(-1, 1))
+    tgt = cm.Domain.from_lat_lon(g["target_lat"], g["target_lon"], kind="sparse" if g["meta"]["target_sparse"] else "dense")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        rec = cm.OrdinaryKrigingReconstructor(src, tgt, n_closest_points=g["meta"]["n_closest_points"], dtype=dtype,
+                                              **g["meta"]["kwargs"])
+        out = rec.reconstruct()
+    got = np.asarray(out.da.values, dtype=np.float64)
+    assert got.shape == g["expected"].shape
+    # the fitted variogram parameters come from the GPU variogram + the same SciPy fit
+    np.testing.assert_allclose(rec.variogram_model_parameters, g["variogram_parameters"], rtol=1e-6, atol=1e-9)
+    scale = np.max(np.abs(g["expected"]))
+    tol = OK_RTOL if dtype == "float64" else 5e-4  # float32 stores values/results at 6e-8 relative
+    assert np.max(np.abs(got - g["expected"])) <= tol * scale
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names("ok_global_") if "gaussian" not in n and "pinv" not in n])
+def test_ok_reconstructor_global_mode_matches_golden(name):
+    """The reference's shipped global kriging (library path, torch.linalg)."""
+    g = load_golden(name)
+    src = sparse_dataset(g["sample_lat"], g["sample_lon"], np.asarray(g["values"]).reshape(-1, 1))
+    tgt = cm.Domain.from_lat_lon(g["target_lat"], g["target_lon"], kind="sparse" if g["meta"]["target_sparse"] else "dense")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = cm.OrdinaryKrigingReconstructor(src, tgt, **g["meta"]["kwargs"]).reconstruct()
+    got = np.asarray(out.da.values, dtype=np.float64)
+    scale = np.max(np.abs(g["expected"]))
+    assert np.max(np.abs(got - g["expected"])) <= OK_RTOL * scale
+
+
+def test_ok_config2_full_size_sample_vs_oracle():
+    """BASELINE config 2: 10 000 samples -> 180x360, k=32, spherical.  The oracle's Python loop is slow,
+    so the full grid is produced on the GPU and every 7th row is checked."""
+    la, lo, v, _ = _samples(10_000, 1235)
+    tl, to = np.arange(-89.5, 90, 1.0), np.arange(-179.5, 180, 1.0)
+    src = static_sparse(la, lo, v)
+    kw = dict(variogram_model="spherical", nlags=6, anisotropy_scaling=1.0)
+    rec = cm.OrdinaryKrigingReconstructor(src, cm.Domain.from_lat_lon(tl, to), n_closest_points=32, **kw)
+    got = np.asarray(rec.reconstruct().da.values)
+    # the oracle normalises targets with their own extrema, so check rows through the full-grid frame
+    ref, model = ok_oracle(la, lo, v, tl, to, False, n_closest_points=None, return_model=True, backend="loop", **kw) if False else (None, None)
+    okr_ref = ok_oracle  # noqa: F841
+    # restated pykrige directly, rows subset, same normalised frame
+    from oracle.ok_oracle import normalize_axis, standardize_values
+
+    *_, s_lat = normalize_axis(la)
+    *_, s_lon = normalize_axis(lo)
+    mean, std, z = standardize_values(v)
+    okr = pk.OrdinaryKriging(s_lon, s_lat, z, **kw)
+    np.testing.assert_allclose(rec.variogram_model_parameters, okr.variogram_model_parameters, rtol=1e-6)
+    *_, t_lat = normalize_axis(tl)
+    *_, t_lon = normalize_axis(to)
+    rows = np.arange(0, 180, 7)
+    zr, _ = okr.execute("grid", t_lon, t_lat[rows], backend="loop", n_closest_points=32)
+    ref = zr * std + mean
+    assert np.max(np.abs(got[rows] - ref)) <= OK_RTOL * np.max(np.abs(ref))
+
+
+def test_kriging_properties():
+    la, lo, v, rng = _samples(600, 41, lat=(-60, 60), lon=(-120, 120))
+    src = static_sparse(la, lo, v)
+    kw = dict(variogram_model="spherical", anisotropy_scaling=1.0, n_closest_points=24)
+    # exact interpolator: predicting at the samples returns the samples (same bbox -> same frame)
+    out = cm.OrdinaryKrigingReconstructor(src, cm.Domain.from_lat_lon(la, lo, kind="sparse"), **kw).reconstruct()
+    np.testing.assert_allclose(out.da.values, v, rtol=0, atol=1e-8)
+    # duplicate coordinates inside a window -> singular system: the reference raises LinAlgError
+    la2, lo2 = la.copy(), lo.copy()
+    la2[1], lo2[1] = la2[0], lo2[0]
+    with pytest.raises(np.linalg.LinAlgError):
+        cm.OrdinaryKrigingReconstructor(static_sparse(la2, lo2, v), cm.Domain.from_lat_lon(la2, lo2, kind="sparse"), **kw).reconstruct()
+    # geographic moving window is not built yet and says so
+    with pytest.raises(NotImplementedError):
+        cm.OrdinaryKrigingReconstructor(src, cm.Domain.from_lat_lon(la, lo, kind="sparse"), coordinates_type="geographic",
+                                        n_closest_points=8).reconstruct()
+
+
+def test_launch_counter_counts_kernels():
+    K.reset_launch_count()
+    la, lo, v, _ = _samples(500, 2)
+    K.idw(la, lo, v, K.Targets.make(np.linspace(-80, 80, 9), np.linspace(-170, 170, 9), True, DEV), k=4)
+    assert K.launch_count() >= 1
