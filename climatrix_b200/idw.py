@@ -52,33 +52,34 @@ def extra_dimensions(domain) -> list:
 
 
 def spatial_values(dataset):
-    """``dataset.da.values`` as (T, N): batch axes first, spatial axes flattened in the order of
-    ``get_all_spatial_points`` (point, or latitude-major grid).  T = 1 for a static dataset."""
+    """``dataset.da.values`` as a 2-D array plus its layout and the batch axes.
+
+    Returns ``(array, layout, batch_axes)``: ``layout == "batch_major"`` -> array is (T, N),
+    ``"sample_major"`` -> (N, T) (no copy when the spatial dimensions lead, e.g. the reference's
+    (point, time) fixtures).  The spatial axis is flattened in the order of
+    ``get_all_spatial_points`` (point, or latitude-major grid).  T = 1 for a static dataset.
+    """
     da = dataset.da
     values = np.asarray(da.values)
     domain = dataset.domain
     dims = [str(d) for d in getattr(da, "dims", ())]
     if len(dims) != values.ndim:  # duck-typed dataset without dims: the reference's flatten (idw.py:135)
-        return values.reshape(1, -1), []
+        return values.reshape(1, -1), "batch_major", []
     name_of = {}
     for kind in domain.all_axes_types:
         ax = domain.get_axis(kind)
         if ax is not None and ax.is_dimension:
             name_of[ax.name] = _axis_kind(kind)
-    if domain.is_sparse:
-        spatial_order = ["point"]
-    else:
-        spatial_order = ["latitude", "longitude"]
+    spatial_order = ["point"] if domain.is_sparse else ["latitude", "longitude"]
     pos_spatial = [dims.index(n) for want in spatial_order for n in dims if name_of.get(n) == want]
     pos_batch = [i for i in range(values.ndim) if i not in pos_spatial]
-    arranged = np.transpose(values, pos_batch + pos_spatial)
     n_batch = int(np.prod([values.shape[i] for i in pos_batch], dtype=np.int64)) if pos_batch else 1
-    batch_axes = []
-    for i in pos_batch:
-        if values.shape[i] > 1:
-            kind = name_of.get(dims[i])
-            batch_axes.append((dims[i], kind, values.shape[i]))
-    return arranged.reshape(n_batch, -1), batch_axes
+    batch_axes = [(dims[i], name_of.get(dims[i]), values.shape[i]) for i in pos_batch if values.shape[i] > 1]
+    if pos_batch and pos_spatial == list(range(len(pos_spatial))) and n_batch > 1:
+        # spatial dimensions lead: (N, T) view, the fast layout of the batched kernel
+        return values.reshape(-1, n_batch), "sample_major", batch_axes
+    arranged = np.transpose(values, pos_batch + pos_spatial)
+    return arranged.reshape(n_batch, -1), "batch_major", batch_axes
 
 
 def wrap_output(target_domain, out_tm: np.ndarray, dataset, batch_axes, name):
@@ -181,7 +182,8 @@ class IDWReconstructor(BaseReconstructor):
         from . import kernels
         from .sharding import idw_on_devices
 
-        values_tn, batch_axes = spatial_values(self.dataset)
+        values_2d, layout, batch_axes = spatial_values(self.dataset)
+        n_batch, n_src = values_2d.shape if layout == "batch_major" else values_2d.shape[::-1]
         spatial_points = self.dataset.domain.get_all_spatial_points()
         if not isinstance(spatial_points, np.ndarray) or spatial_points.ndim != 2 or spatial_points.shape[1] != 2:
             raise ValueError(
@@ -189,25 +191,25 @@ class IDWReconstructor(BaseReconstructor):
                 f"get_all_spatial_points(), but got {type(spatial_points)} "
                 f"with shape {getattr(spatial_points, 'shape', None)}."
             )
-        if values_tn.shape[1] != spatial_points.shape[0]:
+        if n_src != spatial_points.shape[0]:
             raise ValueError(
-                f"dataset holds {values_tn.shape[1]} values per slice for {spatial_points.shape[0]} spatial points"
+                f"dataset holds {n_src} values per slice for {spatial_points.shape[0]} spatial points"
             )
         tgt = self.target_domain
         t_lat = np.ascontiguousarray(tgt.latitude.values, dtype=np.float64)
         t_lon = np.ascontiguousarray(tgt.longitude.values, dtype=np.float64)
         grid = not tgt.is_sparse
         tdtype = torch.float64 if self.dtype == "float64" else torch.float32
-        vals = values_tn[0] if values_tn.shape[0] == 1 else values_tn
+        vals = values_2d.reshape(-1) if n_batch == 1 else values_2d
         log.debug("Querying %d nearest neighbours on the GPU...", self.k)
         out = idw_on_devices(
             np.ascontiguousarray(spatial_points[:, 0], dtype=np.float64),
             np.ascontiguousarray(spatial_points[:, 1], dtype=np.float64),
             vals, t_lat, t_lon, grid, k=self.k, power=self.power, k_min=self.k_min, dtype=tdtype,
-            device=self.device, devices=self.devices,
+            device=self.device, devices=self.devices, layout=layout if n_batch > 1 else None,
         )
         out = np.asarray(out, dtype=np.float64 if self.dtype == "float64" else np.float32)
-        out_tm = out.reshape(values_tn.shape[0], -1)
+        out_tm = out.reshape(n_batch, -1)
         log.debug("Reconstruction completed.")
         wrapped = wrap_output(tgt, out_tm if batch_axes else out_tm[0], self.dataset, batch_axes,
                               getattr(self.dataset.da, "name", None))

@@ -212,6 +212,10 @@ def idw(s_lat, s_lon, values, targets: Targets, *, k: int = 5, power: float = 2.
         values = torch.as_tensor(np.ascontiguousarray(values))
     values = values.to(device=dev, dtype=dtype)
     values, n_batch, layout_code = _values_layout(values, n, layout)
+    if n_batch > 1 and layout_code == _lib.LAYOUT_BATCH_MAJOR:
+        # the batched kernel gathers one sample's whole series per neighbour: give it (N, T) rows
+        values = values.t().contiguous()
+        layout_code = _lib.LAYOUT_SAMPLE_MAJOR
     k, k_min = int(k), int(k_min)
     m = targets.count
     with torch.cuda.device(dev):

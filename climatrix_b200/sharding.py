@@ -36,7 +36,7 @@ def row_shards(n_rows: int, parts: int) -> list[tuple[int, int]]:
 
 
 def idw_on_devices(s_lat, s_lon, values, t_lat, t_lon, grid: bool, *, k: int, power: float, k_min: int,
-                   dtype, device=None, devices=None, return_neighbours: bool = False):
+                   dtype, device=None, devices=None, return_neighbours: bool = False, layout=None):
     """IDW with host (NumPy) inputs and output; H2D and D2H copies included.
 
     values: (N,) or (T, N).  Returns (M,) or (T, M) as a NumPy array.
@@ -50,7 +50,7 @@ def idw_on_devices(s_lat, s_lon, values, t_lat, t_lon, grid: bool, *, k: int, po
         with torch.cuda.device(dev):
             targets = kernels.Targets.make(t_lat, t_lon, grid, dev)
             res = kernels.idw(s_lat, s_lon, values, targets, k=k, power=power, k_min=k_min, dtype=dtype,
-                              return_neighbours=return_neighbours)
+                              return_neighbours=return_neighbours, layout=layout)
             if return_neighbours:
                 out, dist, idx = res
                 return _to_host(out), _to_host(dist), _to_host(idx)
@@ -68,7 +68,7 @@ def idw_on_devices(s_lat, s_lon, values, t_lat, t_lon, grid: bool, *, k: int, po
             lat_band = t_lat[r0:r1]
             lon_band = t_lon if grid else t_lon[r0:r1]
             targets = kernels.Targets.make(lat_band, lon_band, grid, dev)
-            out = kernels.idw(s_lat, s_lon, values, targets, k=k, power=power, k_min=k_min, dtype=dtype)
+            out = kernels.idw(s_lat, s_lon, values, targets, k=k, power=power, k_min=k_min, dtype=dtype, layout=layout)
             pending.append(out)
     parts = [_to_host(o) for o in pending]
     return np.concatenate(parts, axis=-1)
