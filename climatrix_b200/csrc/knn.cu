@@ -32,11 +32,11 @@ namespace {
 
 constexpr int WARPS = 4;
 constexpr int THREADS = WARPS * 32;
-constexpr int TS = 2048;             // samples per shared-memory stage
+constexpr int TS = 1536;             // samples per shared-memory stage
 constexpr int GRP = 32;              // samples per filter group (= one per lane in the re-examination)
 constexpr int CAP = 64;              // candidate slots per target
 constexpr int FLUSH_AT = CAP - GRP;  // re-rank a target once it holds more than this
-constexpr int MAX_CTAS_PER_SM = 2;
+constexpr int MAX_CTAS_PER_SM = 3;
 constexpr int MAX_QPT = 8;
 constexpr int MAX_TQ = WARPS * MAX_QPT * 32;
 constexpr int GMAX = 1024;           // seed grid: at most GMAX x GMAX cells
@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __g
                 float mn[QPT];
 #pragma unroll
                 for (int q = 0; q < QPT; ++q) mn[q] = CMX_INF_F;
-#pragma unroll
+#pragma unroll 2
                 for (int j = 0; j < GRP; j += 4) {
                     const float4 A4 = *reinterpret_cast<const float4*>(cA + g0 + j);
                     const float4 B4 = *reinterpret_cast<const float4*>(cB + g0 + j);

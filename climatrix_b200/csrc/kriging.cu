@@ -121,7 +121,9 @@ __global__ void __launch_bounds__(256) ok_solve_kernel(const OkArgs a, int warps
         // ---- Gauss-Jordan with partial pivoting ----
         unsigned done = 0;  // bit e: my row e*32+lane has been a pivot
         bool singular = false;
-        for (int c = 0; c < k; ++c) {
+        // k == 1: the core is the 1x1 zero matrix while the bordered system [[0,1],[1,0]] is regular
+        // (x = 1, mu = b); handled after the loop
+        for (int c = 0; c < k && k > 1; ++c) {
             double best = -1.0;
             int brow = 0x7fffffff;
 #pragma unroll
@@ -151,12 +153,14 @@ __global__ void __launch_bounds__(256) ok_solve_kernel(const OkArgs a, int warps
             const int p = brow;
             if ((p & 31) == lane) done |= 1u << (p >> 5);
             if (lane == 0) piv[c] = p;
-            const double pinv = 1.0 / mat[(size_t)c * LD + p];
+            // true division: identical rows (duplicate samples, zero nugget) must cancel to exact zeros so
+            // that a singular window is detected, as LAPACK's exact-zero pivot test does for the reference
+            const double pval = mat[(size_t)c * LD + p];
             double f[E];
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const int r = e * 32 + lane;
-                f[e] = (r < k && r != p) ? mat[(size_t)c * LD + r] * pinv : 0.0;
+                f[e] = (r < k && r != p) ? mat[(size_t)c * LD + r] / pval : 0.0;
             }
             __syncwarp();
             for (int cc = c + 1; cc < k + 2; ++cc) {
@@ -171,7 +175,11 @@ __global__ void __launch_bounds__(256) ok_solve_kernel(const OkArgs a, int warps
         }
         // ---- back out x, mu; estimate and variance ----
         double res = quiet_nan<double>(), var = quiet_nan<double>();
-        if (!singular) {
+        if (k == 1) {
+            const double z0 = __shfl_sync(kFull, mz[0], 0), b0 = __shfl_sync(kFull, borig[0], 0);
+            res = z0 * a.out_scale + a.out_shift;
+            var = -(b0 + b0);
+        } else if (!singular) {
             double y[E], u[E];
             double sy = 0.0, su = 0.0;
 #pragma unroll

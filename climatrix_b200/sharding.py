@@ -75,23 +75,62 @@ def idw_on_devices(s_lat, s_lon, values, t_lat, t_lon, grid: bool, *, k: int, po
 
 
 _pinned: dict = {}
+_CHUNK_BYTES = 64 << 20
 
 
 def _to_host(t):
-    """Device -> host through a cached pinned staging buffer (large results)."""
+    """Device -> host NumPy array (freshly owned by the caller).
+
+    Large results are streamed in 64 MiB chunks through two pinned staging buffers: while chunk i+1
+    crosses PCIe, worker threads copy chunk i into the destination array (NumPy releases the GIL for
+    the memcpy), so the pageable-memory copy overlaps the transfer instead of following it.
+    """
+    import threading
+
     import torch
 
-    if t.numel() * t.element_size() < (1 << 22):
+    nbytes = t.numel() * t.element_size()
+    if nbytes < (1 << 22):
         return t.cpu().numpy()
+    t = t.contiguous()
+    flat = t.view(-1)
+    per_chunk = max(1, _CHUNK_BYTES // t.element_size())
     key = (t.dtype, t.device.index)
-    buf = _pinned.get(key)
-    if buf is None or buf.numel() < t.numel():
-        buf = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
-        _pinned[key] = buf
-    view = buf[: t.numel()].view(t.shape)
-    view.copy_(t, non_blocking=True)
-    torch.cuda.current_stream(t.device).synchronize()
-    return view.numpy().copy()
+    stage = _pinned.get(key)
+    if stage is None or stage[0].numel() < per_chunk:
+        stage = [torch.empty(per_chunk, dtype=t.dtype, pin_memory=True) for _ in range(2)]
+        _pinned[key] = stage
+    out = np.empty(t.numel(), dtype=stage[0].numpy().dtype)
+    stream = torch.cuda.current_stream(t.device)
+    events = [torch.cuda.Event(), torch.cuda.Event()]
+    workers: list = [None, None]
+
+    def drain(slot, lo, hi):
+        events[slot].synchronize()
+        src = stage[slot].numpy()
+        n = hi - lo
+        half = n // 2
+        th = threading.Thread(target=np.copyto, args=(out[lo:lo + half], src[:half]))
+        th.start()
+        np.copyto(out[lo + half:hi], src[half:n])
+        th.join()
+
+    n = flat.numel()
+    i = 0
+    for lo in range(0, n, per_chunk):
+        hi = min(n, lo + per_chunk)
+        slot = i & 1
+        if workers[slot] is not None:
+            workers[slot].join()  # the staging buffer is free again
+        stage[slot][: hi - lo].copy_(flat[lo:hi], non_blocking=True)
+        events[slot].record(stream)
+        workers[slot] = threading.Thread(target=drain, args=(slot, lo, hi))
+        workers[slot].start()
+        i += 1
+    for w in workers:
+        if w is not None:
+            w.join()
+    return out.reshape(tuple(t.shape))
 
 
 # --------------------------------------------------------------------------- #
