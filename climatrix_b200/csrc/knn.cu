@@ -32,11 +32,26 @@ namespace {
 
 constexpr int WARPS = 4;
 constexpr int THREADS = WARPS * 32;
-constexpr int TS = 1536;             // samples per shared-memory stage
+#ifndef CMX_TS
+#define CMX_TS 768
+#endif
+#ifndef CMX_CTAS
+#define CMX_CTAS 5
+#endif
+#ifndef CMX_QPT
+#define CMX_QPT 8
+#endif
+#ifndef CMX_UNROLL
+#define CMX_UNROLL 2
+#endif
+#define CMX_STR2(x) #x
+#define CMX_STR(x) CMX_STR2(x)
+#define CMX_UNROLL_PRAGMA CMX_STR(unroll CMX_UNROLL)
+constexpr int TS = CMX_TS;           // samples per shared-memory stage
 constexpr int GRP = 32;              // samples per filter group (= one per lane in the re-examination)
 constexpr int CAP = 64;              // candidate slots per target
 constexpr int FLUSH_AT = CAP - GRP;  // re-rank a target once it holds more than this
-constexpr int MAX_CTAS_PER_SM = 3;
+constexpr int MAX_CTAS_PER_SM = CMX_CTAS;
 constexpr int MAX_QPT = 8;
 constexpr int MAX_TQ = WARPS * MAX_QPT * 32;
 constexpr int GMAX = 1024;           // seed grid: at most GMAX x GMAX cells
@@ -573,7 +588,7 @@ __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __g
                 float mn[QPT];
 #pragma unroll
                 for (int q = 0; q < QPT; ++q) mn[q] = CMX_INF_F;
-#pragma unroll 2
+_Pragma(CMX_UNROLL_PRAGMA)
                 for (int j = 0; j < GRP; j += 4) {
                     const float4 A4 = *reinterpret_cast<const float4*>(cA + g0 + j);
                     const float4 B4 = *reinterpret_cast<const float4*>(cB + g0 + j);
@@ -736,7 +751,7 @@ int run_knn(const KnnJob& job, cudaStream_t stream) {
         return (M + tq - 1) / tq;
     };
     int tiles_c8 = 1, tiles_c2 = 1;
-    const long long t8 = tiles_for(8, tiles_c8);
+    const long long t8 = tiles_for(CMX_QPT, tiles_c8);
     const long long t2 = tiles_for(2, tiles_c2);
     const bool big = t8 >= 2LL * slots;
     const long long tiles = big ? t8 : t2;
@@ -775,9 +790,9 @@ int run_knn(const KnnJob& job, cudaStream_t stream) {
 
     const int e = list_slots(job.k);
     if (big) {
-        if (e == 1) return launch<1, 8>(args, ctas, stream);
-        if (e == 2) return launch<2, 8>(args, ctas, stream);
-        return launch<4, 8>(args, ctas, stream);
+        if (e == 1) return launch<1, CMX_QPT>(args, ctas, stream);
+        if (e == 2) return launch<2, CMX_QPT>(args, ctas, stream);
+        return launch<4, CMX_QPT>(args, ctas, stream);
     }
     if (e == 1) return launch<1, 2>(args, ctas, stream);
     if (e == 2) return launch<2, 2>(args, ctas, stream);
