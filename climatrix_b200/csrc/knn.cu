@@ -32,8 +32,8 @@ namespace {
 
 constexpr int WARPS = 4;
 constexpr int THREADS = WARPS * 32;
-#ifndef CMX_TS
-#define CMX_TS 768
+#ifndef CMX_SS
+#define CMX_SS 256
 #endif
 #ifndef CMX_CTAS
 #define CMX_CTAS 5
@@ -47,13 +47,14 @@ constexpr int THREADS = WARPS * 32;
 #define CMX_STR2(x) #x
 #define CMX_STR(x) CMX_STR2(x)
 #define CMX_UNROLL_PRAGMA CMX_STR(unroll CMX_UNROLL)
-constexpr int TS = CMX_TS;           // samples per shared-memory stage
+constexpr int SS = CMX_SS;           // samples per (warp-private) shared-memory stage
 constexpr int GRP = 32;              // samples per filter group (= one per lane in the re-examination)
 constexpr int CAP = 64;              // candidate slots per target
 constexpr int FLUSH_AT = CAP - GRP;  // re-rank a target once it holds more than this
 constexpr int MAX_CTAS_PER_SM = CMX_CTAS;
 constexpr int MAX_QPT = 8;
 constexpr int MAX_TQ = WARPS * MAX_QPT * 32;
+constexpr size_t WARP_SMEM = 2 * 2 * SS * sizeof(double) + 3 * SS * sizeof(float) + 64;  // raw x2, comp, mbarriers
 constexpr int GMAX = 1024;           // seed grid: at most GMAX x GMAX cells
 constexpr int SAT_LD = GMAX + 1;     // row stride of the summed-area table
 
@@ -304,22 +305,23 @@ __device__ __forceinline__ float filter_threshold(double d2k, float qa, float qb
     return f;
 }
 
+// Tiles are per warp: QPT rows x 32 columns of a dense grid, or QPT*32 consecutive explicit points.
+// ts = q*32 + lane.
 template <int QPT>
 __device__ __forceinline__ bool target_coords(const KnnArgs& a, int tile, int ts, double& ta, double& tb,
                                               long long& m) {
-    constexpr int TQ = WARPS * QPT * 32;
-    constexpr int TR = WARPS * QPT;
+    constexpr int TQW = QPT * 32;
     if (a.j.grid) {
         const int tr = tile / a.tiles_c;
         const int tc = tile - tr * a.tiles_c;
-        const long long row = (long long)tr * TR + (ts >> 5);
+        const long long row = (long long)tr * QPT + (ts >> 5);
         const long long col = (long long)tc * 32 + (ts & 31);
         if (row >= a.j.n_a || col >= a.j.n_b) return false;
         ta = a.j.t_a[row];
         tb = a.j.t_b[col];
         m = row * a.j.n_b + col;
     } else {
-        const long long p = (long long)tile * TQ + ts;
+        const long long p = (long long)tile * TQW + ts;
         if (p >= a.M) return false;
         ta = a.j.t_a[p];
         tb = a.j.t_b[p];
@@ -446,32 +448,41 @@ __device__ __forceinline__ float min3f(float a, float b, float c) {
 // COLSHARE: dense-grid targets -- the QPT targets of a thread sit in one grid column, so the
 // column term  u = |s|^2 - 2 q_b s_b  is evaluated once per sample and thread and each pair
 // costs a single FMA (t = u - 2 q_a s_a).  Explicit target points use the generic two-FMA form.
+//
+// Every warp is an independent worker with a private TMA pipeline: it owns a tile of QPT x 32
+// targets, streams all samples through its own double-buffered shared-memory stage (bulk copies
+// issued by lane 0, completion on the warp's two mbarriers), re-centres them on its tile and
+// filters.  There is no CTA-wide barrier anywhere in the kernel.
 template <int E, int QPT, bool COLSHARE>
 __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __grid_constant__ KnnArgs a) {
-    constexpr int TQ = WARPS * QPT * 32;
+    constexpr int TQW = QPT * 32;  // targets per warp tile
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* raw_a = reinterpret_cast<double*>(smem_raw);
-    double* raw_b = raw_a + TS;
-    float* comp = reinterpret_cast<float*>(raw_b + TS);  // [2][3][TS]
-    __shared__ __align__(8) uint64_t mbar;
-    __shared__ double red[4 * WARPS];
-
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    if (tid == 0) {
-        mbar_init(&mbar, 1);
+
+    // per-warp shared memory: raw[2 buffers][a|b][SS] f64, comp[SS/4][a0..3 b0..3 s0..3] f32, 2 mbarriers
+    unsigned char* wbase = smem_raw + (size_t)warp * WARP_SMEM;
+    double* raw = reinterpret_cast<double*>(wbase);                       // [2][2][SS]
+    float* comp = reinterpret_cast<float*>(wbase + 2 * 2 * SS * sizeof(double));
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(wbase + 2 * 2 * SS * sizeof(double) + 3 * SS * sizeof(float));
+    if (lane == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
         mbar_fence_init();
     }
-    __syncthreads();
-    uint32_t phase = 0;
+    __syncwarp();
+    uint32_t ph0 = 0, ph1 = 0;
+
     const long long n = a.j.n;
-    const int n_st = (int)((n + TS - 1) / TS);
-    const long long slot0 = (long long)blockIdx.x * TQ + (long long)(warp * QPT) * 32;  // + q*32 + lane
+    const int n_st = (int)((n + SS - 1) / SS);
+    const int gwarp = blockIdx.x * WARPS + warp;
+    const int nwarps = gridDim.x * WARPS;
+    const long long slot0 = (long long)gwarp * TQW;  // + q*32 + lane
     const SeedGrid seed = *a.seed;
 
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    for (int tile = gwarp; tile < a.num_tiles; tile += nwarps) {
         // ---------------- targets of this thread ----------------
         float Qa[QPT], Qb[QPT], thr[QPT];
         int off[QPT];
@@ -485,7 +496,7 @@ __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __g
                 long long m;
                 ta[q] = 0.0;
                 tb[q] = q ? tb[0] : 0.0;  // COLSHARE: rows beyond the grid inherit the column coordinate
-                if (target_coords<QPT>(a, tile, (warp * QPT + q) * 32 + lane, ta[q], tb[q], m)) {
+                if (target_coords<QPT>(a, tile, q * 32 + lane, ta[q], tb[q], m)) {
                     validm |= 1u << q;
                     mn_a = fmin(mn_a, ta[q]);
                     mx_a = fmax(mx_a, ta[q]);
@@ -497,20 +508,6 @@ __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __g
             mx_a = warp_max(mx_a);
             mn_b = warp_min(mn_b);
             mx_b = warp_max(mx_b);
-            if (lane == 0) {
-                red[warp * 4 + 0] = mn_a;
-                red[warp * 4 + 1] = mx_a;
-                red[warp * 4 + 2] = mn_b;
-                red[warp * 4 + 3] = mx_b;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) {
-                mn_a = fmin(mn_a, red[w * 4 + 0]);
-                mx_a = fmax(mx_a, red[w * 4 + 1]);
-                mn_b = fmin(mn_b, red[w * 4 + 2]);
-                mx_b = fmax(mx_b, red[w * 4 + 3]);
-            }
             ca = 0.5 * (mn_a + mx_a);  // tile centre: keeps |q|, |s| small where it matters
             cb = 0.5 * (mn_b + mx_b);
 #pragma unroll
@@ -528,39 +525,52 @@ __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __g
 
         // exact re-rank of target (lane L, slot q) of this warp; returns threshold or fused value
         auto rerank = [&](int q, int L, int cnt, bool has, bool final) -> double {
-            const int ts = (warp * QPT + q) * 32 + L;
             double ta = 0.0, tb = 0.0;
             long long m = 0;
-            target_coords<QPT>(a, tile, ts, ta, tb, m);
+            target_coords<QPT>(a, tile, q * 32 + L, ta, tb, m);
             const float qa = __double2float_rn(__dsub_rn(ta, ca));
             const float qb = __double2float_rn(__dsub_rn(tb, cb));
             return rerank_target<E>(a, lane, slot0 + q * 32 + L, ta, tb, m, qa, qb, cnt, has, final);
         };
 
+        auto stage_is_bulk = [&](int st) -> bool {
+            return a.aligned && (n - (long long)st * SS) >= (long long)SS;
+        };
+        auto issue = [&](int st) {  // lane 0: TMA bulk copies of stage st into raw buffer st & 1
+            const int b = st & 1;
+            double* ra = raw + b * 2 * SS;
+            mbar_arrive_expect_tx(&mbar[b], 2u * SS * 8u);
+            tma_load_1d(ra, a.j.s_a + (long long)st * SS, SS * 8u, &mbar[b]);
+            tma_load_1d(ra + SS, a.j.s_b + (long long)st * SS, SS * 8u, &mbar[b]);
+        };
+
         // ---------------- sweep over all samples ----------------
-        if (tid == 0 && a.aligned && n >= TS) {
-            mbar_arrive_expect_tx(&mbar, 2u * TS * 8u);
-            tma_load_1d(raw_a, a.j.s_a, TS * 8u, &mbar);
-            tma_load_1d(raw_b, a.j.s_b, TS * 8u, &mbar);
+        if (lane == 0) {
+            if (n_st > 0 && stage_is_bulk(0)) issue(0);
+            if (n_st > 1 && stage_is_bulk(1)) issue(1);
         }
-        int buf = 0;
         for (int st = 0; st < n_st; ++st) {
-            const long long base = (long long)st * TS;
-            const int cntS = (int)((n - base) < (long long)TS ? (n - base) : (long long)TS);
-            const bool bulk = a.aligned && cntS == TS;
-            float* cA = comp + buf * 3 * TS;
-            float* cB = cA + TS;
-            float* cS = cB + TS;
+            const long long base = (long long)st * SS;
+            const int cntS = (int)((n - base) < (long long)SS ? (n - base) : (long long)SS);
+            const bool bulk = stage_is_bulk(st);
+            const int b = st & 1;
+            const double* ra = raw + b * 2 * SS;
             if (bulk) {
-                mbar_wait(&mbar, phase);
-                phase ^= 1u;
+                if (b == 0) {
+                    mbar_wait(&mbar[0], ph0);
+                    ph0 ^= 1u;
+                } else {
+                    mbar_wait(&mbar[1], ph1);
+                    ph1 ^= 1u;
+                }
             }
-            // re-centre on the tile, round to fp32, precompute |s|^2
-            for (int i = tid; i < TS; i += THREADS) {
+            // re-centre on the tile, round to fp32, precompute |s|^2; layout [i/4][a0..3 b0..3 s0..3]
+#pragma unroll
+            for (int i = lane; i < SS; i += 32) {
                 double xa, xb;
                 if (bulk) {
-                    xa = raw_a[i];
-                    xb = raw_b[i];
+                    xa = ra[i];
+                    xb = ra[SS + i];
                 } else if (i < cntS) {
                     xa = a.j.s_a[base + i];
                     xb = a.j.s_b[base + i];
@@ -569,16 +579,13 @@ __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __g
                 }
                 const float fa = __double2float_rn(__dsub_rn(xa, ca));
                 const float fb = __double2float_rn(__dsub_rn(xb, cb));
-                cA[i] = fa;
-                cB[i] = fb;
-                cS[i] = fmaf(fb, fb, fa * fa);
+                float* dst = comp + (i >> 2) * 12 + (i & 3);
+                dst[0] = fa;
+                dst[4] = fb;
+                dst[8] = fmaf(fb, fb, fa * fa);
             }
-            __syncthreads();  // stage complete; raw buffers free again
-            if (tid == 0 && st + 1 < n_st && a.aligned && (n - (base + TS)) >= (long long)TS) {
-                mbar_arrive_expect_tx(&mbar, 2u * TS * 8u);
-                tma_load_1d(raw_a, a.j.s_a + base + TS, TS * 8u, &mbar);
-                tma_load_1d(raw_b, a.j.s_b + base + TS, TS * 8u, &mbar);
-            }
+            __syncwarp();  // stage complete; raw buffer b is free again
+            if (lane == 0 && st + 2 < n_st && stage_is_bulk(st + 2)) issue(st + 2);
 
             const int cnt_pad = (cntS + GRP - 1) & ~(GRP - 1);
             const unsigned jbase = (unsigned)base;
@@ -588,11 +595,12 @@ __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __g
                 float mn[QPT];
 #pragma unroll
                 for (int q = 0; q < QPT; ++q) mn[q] = CMX_INF_F;
-_Pragma(CMX_UNROLL_PRAGMA)
-                for (int j = 0; j < GRP; j += 4) {
-                    const float4 A4 = *reinterpret_cast<const float4*>(cA + g0 + j);
-                    const float4 B4 = *reinterpret_cast<const float4*>(cB + g0 + j);
-                    const float4 S4 = *reinterpret_cast<const float4*>(cS + g0 + j);
+                const float4* cg = reinterpret_cast<const float4*>(comp + (g0 >> 2) * 12);
+                _Pragma(CMX_UNROLL_PRAGMA)
+                for (int j = 0; j < GRP / 4; ++j) {
+                    const float4 A4 = cg[3 * j + 0];
+                    const float4 B4 = cg[3 * j + 1];
+                    const float4 S4 = cg[3 * j + 2];
                     if (COLSHARE) {
                         float u0, u1, u2, u3;
                         fma2_bcast(Qb[0], B4.x, B4.y, S4.x, S4.y, u0, u1);
@@ -621,12 +629,13 @@ _Pragma(CMX_UNROLL_PRAGMA)
                 for (int q = 0; q < QPT; ++q) {
                     unsigned hit = __ballot_sync(kFull, mn[q] < thr[q]);
                     if (hit) {
-                        const float xa = cA[g0 + lane], xb = cB[g0 + lane], xs = cS[g0 + lane];
+                        const float* cs = comp + ((g0 + lane) >> 2) * 12 + (lane & 3);
+                        const float xa = cs[0], xb = cs[4], xs = cs[8];
                         do {
                             const int L = __ffs(hit) - 1;
                             hit &= hit - 1;
                             const float qa2 = __shfl_sync(kFull, Qa[q], L);
-                            const float qb2 = __shfl_sync(kFull, Qb[q], L);
+                            const float qb2 = __shfl_sync(kFull, Qb[COLSHARE ? 0 : q], L);
                             const float th = __shfl_sync(kFull, thr[q], L);
                             const int o = __shfl_sync(kFull, off[q], L);
                             const float t = fmaf(qa2, xa, fmaf(qb2, xb, xs));
@@ -654,7 +663,7 @@ _Pragma(CMX_UNROLL_PRAGMA)
                     }
                 }
             }
-            buf ^= 1;
+            __syncwarp();  // all lanes done with comp before the next stage overwrites it
         }
 
         // ---------------- final re-rank + epilogue ----------------
@@ -679,7 +688,7 @@ _Pragma(CMX_UNROLL_PRAGMA)
                 if ((validm >> q) & 1u) {
                     double ta, tb;
                     long long m;
-                    target_coords<QPT>(a, tile, (warp * QPT + q) * 32 + lane, ta, tb, m);
+                    target_coords<QPT>(a, tile, q * 32 + lane, ta, tb, m);
                     if (a.j.value_is_f32)
                         static_cast<float*>(a.j.out)[m] = (float)res[q];
                     else
@@ -692,7 +701,7 @@ _Pragma(CMX_UNROLL_PRAGMA)
 
 template <int E, int QPT>
 int launch(const KnnArgs& args, int ctas, cudaStream_t stream) {
-    const size_t smem = 2 * TS * sizeof(double) + 6 * TS * sizeof(float);
+    const size_t smem = WARPS * WARP_SMEM;
     timing_begin(CMX_KERNEL_KNN, stream);
     if (args.j.grid) {
         CMX_CUDA(cudaFuncSetAttribute(knn_kernel<E, QPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -741,24 +750,24 @@ int run_knn(const KnnJob& job, cudaStream_t stream) {
 
     // Large tiles (8 targets per thread) amortise the shared-memory loads best; fall back to
     // 2 per thread when that would leave SMs idle.
-    auto tiles_for = [&](int qpt, int& tiles_c) -> long long {
-        const int tr = WARPS * qpt, tq = WARPS * qpt * 32;
+    auto tiles_for = [&](int qpt, int& tiles_c) -> long long {  // warp tiles: qpt rows x 32 columns
         if (job.grid) {
             tiles_c = (int)((job.n_b + 31) / 32);
-            return ((job.n_a + tr - 1) / tr) * (long long)tiles_c;
+            return ((job.n_a + qpt - 1) / qpt) * (long long)tiles_c;
         }
         tiles_c = 1;
-        return (M + tq - 1) / tq;
+        return (M + qpt * 32 - 1) / (qpt * 32);
     };
     int tiles_c8 = 1, tiles_c2 = 1;
     const long long t8 = tiles_for(CMX_QPT, tiles_c8);
     const long long t2 = tiles_for(2, tiles_c2);
-    const bool big = t8 >= 2LL * slots;
+    const bool big = t8 >= 2LL * slots * WARPS;
     const long long tiles = big ? t8 : t2;
     if (tiles > 0x7fffffffLL) return CMX_ERR_TOO_MANY;
     args.tiles_c = big ? tiles_c8 : tiles_c2;
     args.num_tiles = (int)tiles;
-    const int ctas = (int)(tiles < slots ? tiles : slots);
+    const long long ctas_needed = (tiles + WARPS - 1) / WARPS;
+    const int ctas = (int)(ctas_needed < slots ? ctas_needed : slots);
 
     // workspace: [seed grid | lists d | candidates | lists i]
     const size_t kp = 32 * (size_t)list_slots(job.k);
