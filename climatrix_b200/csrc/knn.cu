@@ -484,8 +484,10 @@ __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __g
 
     for (int tile = gwarp; tile < a.num_tiles; tile += nwarps) {
         // ---------------- targets of this thread ----------------
-        float Qa[QPT], Qb[QPT], thr[QPT];
-        int off[QPT];
+        float Qa[QPT], Qb[COLSHARE ? 1 : QPT], thr[QPT];
+        unsigned offp[(QPT + 3) / 4];  // candidate counts, 8 bits per target (<= CAP = 64)
+#pragma unroll
+        for (int i = 0; i < (QPT + 3) / 4; ++i) offp[i] = 0u;
         unsigned validm = 0, has_list = 0;
         double ca, cb;
         {
@@ -516,10 +518,10 @@ __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __g
                 const float qa = __double2float_rn(__dsub_rn(ta[q], ca));
                 const float qb = __double2float_rn(__dsub_rn(tb[q], cb));
                 Qa[q] = ok ? -2.0f * qa : 0.0f;
-                Qb[q] = (ok || COLSHARE) ? -2.0f * qb : 0.0f;
+                if (!COLSHARE) Qb[q] = ok ? -2.0f * qb : 0.0f;
+                else if (q == 0) Qb[0] = -2.0f * qb;  // one column per thread
                 // rigorous starting threshold from the sample-count grid (never below the true k-th distance)
                 thr[q] = ok ? filter_threshold(seed_bound_d2(seed, a.sat, ta[q], tb[q], a.j.k), qa, qb) : -CMX_INF_F;
-                off[q] = 0;
             }
         }
 
@@ -637,7 +639,7 @@ __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __g
                             const float qa2 = __shfl_sync(kFull, Qa[q], L);
                             const float qb2 = __shfl_sync(kFull, Qb[COLSHARE ? 0 : q], L);
                             const float th = __shfl_sync(kFull, thr[q], L);
-                            const int o = __shfl_sync(kFull, off[q], L);
+                            const int o = (int)((__shfl_sync(kFull, offp[q >> 2], L) >> ((q & 3) * 8)) & 0xffu);
                             const float t = fmaf(qa2, xa, fmaf(qb2, xb, xs));
                             const bool pass = t < th;
                             const unsigned pm = __ballot_sync(kFull, pass);
@@ -653,7 +655,7 @@ __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __g
                                 no = 0;
                             }
                             if (lane == L) {
-                                off[q] = no;
+                                offp[q >> 2] = (offp[q >> 2] & ~(0xffu << ((q & 3) * 8))) | ((unsigned)no << ((q & 3) * 8));
                                 if (full) {
                                     thr[q] = nthr;
                                     has_list |= 1u << q;
@@ -676,7 +678,7 @@ __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __g
             while (need) {
                 const int L = __ffs(need) - 1;
                 need &= need - 1;
-                const int cnt = __shfl_sync(kFull, off[q], L);
+                const int cnt = (int)((__shfl_sync(kFull, offp[q >> 2], L) >> ((q & 3) * 8)) & 0xffu);
                 const bool has = (__shfl_sync(kFull, has_list, L) >> q) & 1u;
                 const double r = rerank(q, L, cnt, has, true);
                 if (lane == L) res[q] = r;
@@ -758,13 +760,17 @@ int run_knn(const KnnJob& job, cudaStream_t stream) {
         tiles_c = 1;
         return (M + qpt * 32 - 1) / (qpt * 32);
     };
-    int tiles_c8 = 1, tiles_c2 = 1;
+    // 8 targets per thread amortise the shared-memory loads best (large problems); small problems are
+    // latency bound (per-target re-ranks are serial inside a warp), so they get fewer targets per warp.
+    int tiles_c8 = 1, tiles_c2 = 1, tiles_c1 = 1;
     const long long t8 = tiles_for(CMX_QPT, tiles_c8);
     const long long t2 = tiles_for(2, tiles_c2);
-    const bool big = t8 >= 2LL * slots * WARPS;
-    const long long tiles = big ? t8 : t2;
+    const long long t1 = tiles_for(1, tiles_c1);
+    const long long total_warps = (long long)slots * WARPS;
+    const int qpt = t8 >= 2 * total_warps ? CMX_QPT : (t2 >= total_warps ? 2 : 1);
+    const long long tiles = qpt == CMX_QPT ? t8 : (qpt == 2 ? t2 : t1);
     if (tiles > 0x7fffffffLL) return CMX_ERR_TOO_MANY;
-    args.tiles_c = big ? tiles_c8 : tiles_c2;
+    args.tiles_c = qpt == CMX_QPT ? tiles_c8 : (qpt == 2 ? tiles_c2 : tiles_c1);
     args.num_tiles = (int)tiles;
     const long long ctas_needed = (tiles + WARPS - 1) / WARPS;
     const int ctas = (int)(ctas_needed < slots ? ctas_needed : slots);
@@ -798,14 +804,19 @@ int run_knn(const KnnJob& job, cudaStream_t stream) {
     if (rc != CMX_OK) return rc;
 
     const int e = list_slots(job.k);
-    if (big) {
+    if (qpt == CMX_QPT) {
         if (e == 1) return launch<1, CMX_QPT>(args, ctas, stream);
         if (e == 2) return launch<2, CMX_QPT>(args, ctas, stream);
         return launch<4, CMX_QPT>(args, ctas, stream);
     }
-    if (e == 1) return launch<1, 2>(args, ctas, stream);
-    if (e == 2) return launch<2, 2>(args, ctas, stream);
-    return launch<4, 2>(args, ctas, stream);
+    if (qpt == 2) {
+        if (e == 1) return launch<1, 2>(args, ctas, stream);
+        if (e == 2) return launch<2, 2>(args, ctas, stream);
+        return launch<4, 2>(args, ctas, stream);
+    }
+    if (e == 1) return launch<1, 1>(args, ctas, stream);
+    if (e == 2) return launch<2, 1>(args, ctas, stream);
+    return launch<4, 1>(args, ctas, stream);
 }
 
 }  // namespace cmx

@@ -224,6 +224,182 @@ __global__ void __launch_bounds__(256) ok_solve_kernel(const OkArgs a, int warps
     }
 }
 
+// k > 32: W warps (a "team") solve one target together, one row per lane (row = wsub*32 + lane).
+// Same algorithm as above; the team synchronises once per elimination step on its own named
+// barrier.  Doubling the warps per window doubles the parallelism available to hide the
+// shared-memory round trips, at the same shared-memory footprint per window.
+__device__ __forceinline__ void team_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <int W, typename V>
+__global__ void __launch_bounds__(512) ok_solve_team_kernel(const OkArgs a, int teams_per_cta) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int LD = 32 * W;
+    const int k = a.k;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int team = warp / W, wsub = warp % W;
+    const int r = wsub * 32 + lane;  // my row (and my column in the final extraction)
+    const size_t per_team = (size_t)(k + 2) * LD * sizeof(double) + 2 * LD * sizeof(double) + LD * sizeof(int) +
+                            2 * W * 16 + 4 * W * sizeof(double);
+    unsigned char* base = smem_raw + (size_t)team * per_team;
+    double* mat = reinterpret_cast<double*>(base);
+    double* cx = mat + (size_t)(k + 2) * LD;
+    double* cy = cx + LD;
+    double* pbest = cy + LD;                            // [2][W] partial maxima (double-buffered by step parity)
+    double* red = pbest + 2 * W;                        // [4][W] partial sums
+    int* prow = reinterpret_cast<int*>(red + 4 * W);    // [2][W] partial arg-max rows
+    int* piv = prow + 2 * W;                            // [LD]
+    double* colB = mat + (size_t)k * LD;
+    double* colO = mat + (size_t)(k + 1) * LD;
+    const int bar_id = 1 + team, bar_n = 32 * W;
+
+    const long long total_teams = (long long)gridDim.x * teams_per_cta;
+    for (long long m = (long long)blockIdx.x * teams_per_cta + team; m < a.M; m += total_teams) {
+        double mx = 0.0, my = 0.0, mz = 0.0, borig = 0.0;
+        if (r < k) {
+            const int id = a.idx[m * k + r];
+            mx = a.s_x[id];
+            my = a.s_y[id];
+            mz = a.z_is_f32 ? (double)static_cast<const float*>(a.z)[id] : static_cast<const double*>(a.z)[id];
+            const double bd = sqrt(a.d2[m * k + r]);
+            double b = -gamma_of(a.model, a.p0, a.p1, a.p2, bd);
+            if (a.exact_values && fabs(bd) <= OK_EPS) b = 0.0;
+            borig = b;
+            cx[r] = mx;
+            cy[r] = my;
+            colB[r] = b;
+            colO[r] = 1.0;
+        }
+        team_sync(bar_id, bar_n);
+        if (r < k) {
+            for (int j = 0; j < k; ++j) {
+                const double dx = __dsub_rn(mx, cx[j]), dy = __dsub_rn(my, cy[j]);
+                const double d = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                mat[(size_t)j * LD + r] = (r == j) ? 0.0 : -gamma_of(a.model, a.p0, a.p1, a.p2, d);
+            }
+        }
+        bool done = false, singular = false;
+        for (int c = 0; c < k; ++c) {
+            double best = -1.0;
+            int brow = 0x7fffffff;
+            if (r < k && !done) {
+                best = fabs(mat[(size_t)c * LD + r]);
+                brow = r;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(kFull, best, o);
+                const int orow = __shfl_xor_sync(kFull, brow, o);
+                if (ob > best || (ob == best && orow < brow)) {
+                    best = ob;
+                    brow = orow;
+                }
+            }
+            const int pb = (c & 1) * W;
+            if (lane == 0) {
+                pbest[pb + wsub] = best;
+                prow[pb + wsub] = brow;
+            }
+            team_sync(bar_id, bar_n);  // step c-1 updates of every warp are complete and visible
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                const double ob = pbest[pb + w];
+                const int orow = prow[pb + w];
+                if (ob > best || (ob == best && orow < brow)) {
+                    best = ob;
+                    brow = orow;
+                }
+            }
+            if (!(best > 0.0)) {
+                singular = true;
+                break;
+            }
+            const int p = brow;
+            if (r == p) done = true;
+            if (r == 0) piv[c] = p;
+            const double pval = mat[(size_t)c * LD + p];
+            const bool upd = r < k && r != p;
+            const double f = upd ? mat[(size_t)c * LD + r] / pval : 0.0;
+            if (upd) {
+                for (int cc = c + 1; cc < k + 2; ++cc)
+                    mat[(size_t)cc * LD + r] = fma(-f, mat[(size_t)cc * LD + p], mat[(size_t)cc * LD + r]);
+            }
+        }
+        team_sync(bar_id, bar_n);
+        double res = quiet_nan<double>(), var = quiet_nan<double>();
+        if (!singular) {
+            double y = 0.0, u = 0.0;
+            if (r < k) {  // r plays the role of the column index here
+                const int p = piv[r];
+                const double dinv = 1.0 / mat[(size_t)r * LD + p];
+                y = colB[p] * dinv;
+                u = colO[p] * dinv;
+            }
+            const double sy_w = warp_sum(y), su_w = warp_sum(u);
+            if (lane == 0) {
+                red[0 * W + wsub] = sy_w;
+                red[1 * W + wsub] = su_w;
+            }
+            team_sync(bar_id, bar_n);
+            double sy = 0.0, su = 0.0;
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                sy += red[0 * W + w];
+                su += red[1 * W + w];
+            }
+            const double mu = (sy - 1.0) / su;
+            const double x = y - mu * u;
+            const double zz_w = warp_sum(x * mz), xb_w = warp_sum(x * borig);
+            if (lane == 0) {
+                red[2 * W + wsub] = zz_w;
+                red[3 * W + wsub] = xb_w;
+            }
+            team_sync(bar_id, bar_n);
+            double zz = 0.0, xb = 0.0;
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                zz += red[2 * W + w];
+                xb += red[3 * W + w];
+            }
+            res = zz * a.out_scale + a.out_shift;
+            var = -(xb + mu);
+            if (!isfinite(mu)) singular = true;
+        }
+        if (r == 0) {
+            if (singular) {
+                res = quiet_nan<double>();
+                var = quiet_nan<double>();
+                if (a.n_singular) atomicAdd(a.n_singular, 1);
+            }
+            static_cast<V*>(a.out)[m] = (V)res;
+            if (a.sigmasq) static_cast<V*>(a.sigmasq)[m] = (V)var;
+        }
+        team_sync(bar_id, bar_n);  // shared memory of the team is reused by the next window
+    }
+}
+
+template <int W, typename V>
+int launch_ok_team(const OkArgs& a, cudaStream_t stream) {
+    const int k = a.k;
+    const size_t per_team = (size_t)(k + 2) * 32 * W * sizeof(double) + 2 * 32 * W * sizeof(double) + 32 * W * sizeof(int) +
+                            2 * W * 16 + 4 * W * sizeof(double);
+    int teams = (int)((200 * 1024) / per_team);
+    const int max_teams = 512 / (32 * W) < 15 ? 512 / (32 * W) : 15;  // <= 16 warps per CTA, <= 15 named barriers
+    teams = teams > max_teams ? max_teams : (teams < 1 ? 1 : teams);
+    const size_t smem = per_team * teams;
+    CMX_CUDA(cudaFuncSetAttribute(ok_solve_team_kernel<W, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long ctas = (a.M + teams - 1) / teams;
+    const long long cap = (long long)sm_count() * 4;
+    if (ctas > cap) ctas = cap;
+    timing_begin(CMX_KERNEL_OK_SOLVE, stream);
+    ok_solve_team_kernel<W, V><<<(unsigned)ctas, teams * W * 32, smem, stream>>>(a, teams);
+    timing_end(CMX_KERNEL_OK_SOLVE, stream);
+    note_launch();
+    return check_launch();
+}
+
 template <int E, typename V>
 int launch_ok(const OkArgs& a, cudaStream_t stream) {
     const int k = a.k;
@@ -301,8 +477,8 @@ int ok_entry(const double* s_x, const double* s_y, const V* z, int64_t n, const 
     a.sigmasq = sigmasq;
     a.n_singular = n_singular;
     if (k <= 32) return launch_ok<1, V>(a, stream);
-    if (k <= 64) return launch_ok<2, V>(a, stream);
-    return launch_ok<4, V>(a, stream);
+    if (k <= 64) return launch_ok_team<2, V>(a, stream);
+    return launch_ok_team<4, V>(a, stream);
 }
 
 }  // namespace
