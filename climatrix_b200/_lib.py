@@ -38,6 +38,9 @@ SIGNATURES = {
     "cmx_timing_reset": (None, []),
     "cmx_timing_read": (c_int, [c_int, ctypes.POINTER(c_double), ctypes.POINTER(c_i64)]),
     "cmx_fp32_peak_tflops": (c_double, []),
+    "cmx_knn3": (c_int, [_P, _P, _P, c_i64, _P, _P, _P, c_i64, c_int, _P, _P, _P]),
+    "cmx_ok_solve_f64": (c_int, [_P, _P, _P, c_i64, _P, _P, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_double), c_int, c_double, c_double, _P, _P, _P, _P]),
+    "cmx_ok_solve_f32": (c_int, [_P, _P, _P, c_i64, _P, _P, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_double), c_int, c_double, c_double, _P, _P, _P, _P]),
     "cmx_launch_count": (c_i64, []),
     "cmx_reset_launch_count": (None, []),
 }

@@ -16,8 +16,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.environ.get("CMX_LIB") or os.path.join(LIB_DIR, "libclimatrix_b200.so")  # CMX_LIB: tuning variants
-SOURCES = ["capi.cu", "knn.cu", "idw.cu", "variogram.cu", "kriging.cu"]
-HEADERS = ["common.cuh", os.path.join("..", "..", "include", "climatrix_b200.h")]
+SOURCES = ["capi.cu", "knn.cu", "knn3.cu", "idw.cu", "variogram.cu", "kriging.cu"]
+HEADERS = ["common.cuh", "rerank.cuh", os.path.join("..", "..", "include", "climatrix_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

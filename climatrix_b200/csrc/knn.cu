@@ -26,6 +26,7 @@
 #include <limits.h>
 
 #include "common.cuh"
+#include "rerank.cuh"
 
 namespace cmx {
 namespace {
@@ -55,7 +56,13 @@ constexpr int MAX_CTAS_PER_SM = CMX_CTAS;
 constexpr int MAX_QPT = 8;
 constexpr int MAX_TQ = WARPS * MAX_QPT * 32;
 constexpr size_t WARP_SMEM = 2 * 2 * SS * sizeof(double) + 3 * SS * sizeof(float) + 64;  // raw x2, comp, mbarriers
-constexpr int GMAX = 1024;           // seed grid: at most GMAX x GMAX cells
+#ifndef CMX_GMAX
+#define CMX_GMAX 2048
+#endif
+#ifndef CMX_SEED_C0
+#define CMX_SEED_C0 0.5
+#endif
+constexpr int GMAX = CMX_GMAX;       // seed grid: at most GMAX x GMAX cells
 constexpr int SAT_LD = GMAX + 1;     // row stride of the summed-area table
 
 #define CMX_INF __longlong_as_double(0x7ff0000000000000LL)
@@ -122,11 +129,11 @@ __global__ void seed_geometry_kernel(const double* bbox, long long n, SeedGrid* 
     s.a0 = bbox[0];
     s.b0 = bbox[2];
     s.valid = (ea >= 0.0 && eb >= 0.0 && isfinite(ea) && isfinite(eb)) ? 1 : 0;
-    // about two samples per cell, at most GMAX cells per axis
+    // about CMX_SEED_C0 samples per cell, at most GMAX cells per axis
     double h = 0.0;
     if (s.valid) {
         const double area = (ea > 0 ? ea : 1.0) * (eb > 0 ? eb : 1.0);
-        h = sqrt(2.0 * area / (double)(n > 0 ? n : 1));
+        h = sqrt(CMX_SEED_C0 * area / (double)(n > 0 ? n : 1));
         h = fmax(h, fmax(ea, eb) / (double)(GMAX - 1));
         if (!(h > 0.0)) h = 1.0;
     } else {
@@ -221,73 +228,6 @@ __device__ __forceinline__ double seed_bound_d2(const SeedGrid& s, const int* __
 // ------------------------------------------------------------------------------------------
 // exact re-rank machinery
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool lex_less(double da, int ia, double db, int ib) {
-    return da < db || (da == db && ia < ib);
-}
-
-// ascending bitonic sort of one (d, i) element per lane
-__device__ __forceinline__ void warp_sort32(double& d, int& i, int lane) {
-#pragma unroll
-    for (int k2 = 2; k2 <= 32; k2 <<= 1) {
-#pragma unroll
-        for (int j = k2 >> 1; j > 0; j >>= 1) {
-            const double pd = __shfl_xor_sync(kFull, d, j);
-            const int pi = __shfl_xor_sync(kFull, i, j);
-            const bool up = (lane & k2) == 0;
-            const bool lower = (lane & j) == 0;
-            const bool p_less = lex_less(pd, pi, d, i);
-            const bool take = (lower == up) ? p_less : !p_less;
-            if (take) {
-                d = pd;
-                i = pi;
-            }
-        }
-    }
-}
-
-// list: KP = 32*E elements, element e*32+lane in (ld[e], li[e]), ascending.
-// (cd, ci): 32 sorted candidates, one per lane.  Keeps the KP smallest, sorted.
-template <int E>
-__device__ __forceinline__ void merge_sorted32(double (&ld)[E], int (&li)[E], double cd, int ci, int lane) {
-    // min(list[i], cand_reversed[i]) over the top 32 slots -> bitonic sequence of the KP smallest
-    const double rd = __shfl_sync(kFull, cd, 31 - lane);
-    const int ri = __shfl_sync(kFull, ci, 31 - lane);
-    if (lex_less(rd, ri, ld[E - 1], li[E - 1])) {
-        ld[E - 1] = rd;
-        li[E - 1] = ri;
-    }
-#pragma unroll
-    for (int j = E / 2; j >= 1; j >>= 1) {  // strides of j*32 elements stay inside a lane
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            if ((e & j) == 0 && e + j < E) {
-                if (lex_less(ld[e + j], li[e + j], ld[e], li[e])) {
-                    const double td = ld[e];
-                    const int ti = li[e];
-                    ld[e] = ld[e + j];
-                    li[e] = li[e + j];
-                    ld[e + j] = td;
-                    li[e + j] = ti;
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int j = 16; j >= 1; j >>= 1) {
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const double pd = __shfl_xor_sync(kFull, ld[e], j);
-            const int pi = __shfl_xor_sync(kFull, li[e], j);
-            const bool lower = (lane & j) == 0;
-            const bool p_less = lex_less(pd, pi, ld[e], li[e]);
-            if (lower ? p_less : !p_less) {
-                ld[e] = pd;
-                li[e] = pi;
-            }
-        }
-    }
-}
-
 // Conservative fp32 filter threshold for "exact d2 <= d2k" in t-space (t = d2 - |q|^2).
 // Error model (DESIGN.md "filter margin"): coordinates are rounded to fp32 after
 // centring (relative 2^-24 each), S = fma(b,b,a*a), t = fma(Qa,a,fma(Qb,b,S)).

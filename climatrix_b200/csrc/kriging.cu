@@ -37,6 +37,7 @@ struct OkArgs {
     int model;
     double p0, p1, p2;
     int exact_values;
+    int metric;  // CMX_METRIC_EUCLIDEAN: d2 = squared Euclidean; GEOGRAPHIC: d2 = squared chord, s_x = lon, s_y = lat (degrees)
     double out_scale, out_shift;
     void* out;
     void* sigmasq;
@@ -60,6 +61,18 @@ __device__ __forceinline__ double gamma_of(int model, double p0, double p1, doub
         default:  // exponential: psill (1 - exp(-d / (range/3))) + nugget
             return p0 * (1.0 - exp(-d / (p1 / 3.0))) + p2;
     }
+}
+
+// distance target -> neighbour from the stored squared distance of the neighbour search
+__device__ __forceinline__ double window_distance(int metric, double d2) {
+    const double d = sqrt(d2);
+    return metric == CMX_METRIC_GEOGRAPHIC ? chord_to_great_circle_deg(d) : d;
+}
+// distance between two samples of the window (pykrige _get_kriging_matrix: cdist / great_circle_distance)
+__device__ __forceinline__ double sample_distance(int metric, double xi, double yi, double xj, double yj) {
+    if (metric == CMX_METRIC_GEOGRAPHIC) return great_circle_deg(xi, yi, xj, yj);
+    const double dx = __dsub_rn(xi, xj), dy = __dsub_rn(yi, yj);
+    return sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
 }
 
 // E = ceil(k / 32) rows per lane; ld = 32 * E (column stride, in doubles)
@@ -93,7 +106,7 @@ __global__ void __launch_bounds__(256) ok_solve_kernel(const OkArgs a, int warps
                 mx[e] = a.s_x[id];
                 my[e] = a.s_y[id];
                 mz[e] = a.z_is_f32 ? (double)static_cast<const float*>(a.z)[id] : static_cast<const double*>(a.z)[id];
-                const double bd = sqrt(a.d2[m * k + r]);
+                const double bd = window_distance(a.metric, a.d2[m * k + r]);
                 double b = -gamma_of(a.model, a.p0, a.p1, a.p2, bd);
                 if (a.exact_values && fabs(bd) <= OK_EPS) b = 0.0;
                 borig[e] = b;
@@ -111,8 +124,7 @@ __global__ void __launch_bounds__(256) ok_solve_kernel(const OkArgs a, int warps
             for (int e = 0; e < E; ++e) {
                 const int r = e * 32 + lane;
                 if (r < k) {
-                    const double dx = __dsub_rn(mx[e], xj), dy = __dsub_rn(my[e], yj);
-                    const double d = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                    const double d = sample_distance(a.metric, mx[e], my[e], xj, yj);
                     mat[(size_t)j * LD + r] = (r == j) ? 0.0 : -gamma_of(a.model, a.p0, a.p1, a.p2, d);
                 }
             }
@@ -263,7 +275,7 @@ __global__ void __launch_bounds__(512) ok_solve_team_kernel(const OkArgs a, int 
             mx = a.s_x[id];
             my = a.s_y[id];
             mz = a.z_is_f32 ? (double)static_cast<const float*>(a.z)[id] : static_cast<const double*>(a.z)[id];
-            const double bd = sqrt(a.d2[m * k + r]);
+            const double bd = window_distance(a.metric, a.d2[m * k + r]);
             double b = -gamma_of(a.model, a.p0, a.p1, a.p2, bd);
             if (a.exact_values && fabs(bd) <= OK_EPS) b = 0.0;
             borig = b;
@@ -275,8 +287,7 @@ __global__ void __launch_bounds__(512) ok_solve_team_kernel(const OkArgs a, int 
         team_sync(bar_id, bar_n);
         if (r < k) {
             for (int j = 0; j < k; ++j) {
-                const double dx = __dsub_rn(mx, cx[j]), dy = __dsub_rn(my, cy[j]);
-                const double d = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                const double d = sample_distance(a.metric, mx, my, cx[j], cy[j]);
                 mat[(size_t)j * LD + r] = (r == j) ? 0.0 : -gamma_of(a.model, a.p0, a.p1, a.p2, d);
             }
         }
@@ -418,6 +429,49 @@ int launch_ok(const OkArgs& a, cudaStream_t stream) {
     return check_launch();
 }
 
+// K4 on an existing neighbour table
+template <typename V>
+int solve_table(const double* s_x, const double* s_y, const V* z, const int* idx, const double* d2, long long M,
+                int metric, int k, int model, const double* params, int exact_values, double out_scale,
+                double out_shift, V* out, V* sigmasq, int32_t* n_singular, cudaStream_t stream) {
+    if (M == 0) return CMX_OK;
+    OkArgs a;
+    a.s_x = s_x;
+    a.s_y = s_y;
+    a.z = z;
+    a.z_is_f32 = sizeof(V) == 4;
+    a.idx = idx;
+    a.d2 = d2;
+    a.M = M;
+    a.k = k;
+    a.model = model;
+    a.p0 = params[0];
+    a.p1 = params[1];
+    a.p2 = params[2];
+    a.exact_values = exact_values;
+    a.metric = metric;
+    a.out_scale = out_scale;
+    a.out_shift = out_shift;
+    a.out = out;
+    a.sigmasq = sigmasq;
+    a.n_singular = n_singular;
+    if (k <= 32) return launch_ok<1, V>(a, stream);
+    if (k <= 64) return launch_ok_team<2, V>(a, stream);
+    return launch_ok_team<4, V>(a, stream);
+}
+
+template <typename V>
+int solve_entry(const double* s_x, const double* s_y, const V* z, int64_t n, const int32_t* idx, const double* d2,
+                int64_t M, int metric, int k, int model, const double* params, int exact_values, double out_scale,
+                double out_shift, V* out, V* sigmasq, int32_t* n_singular, void* stream) {
+    if (!s_x || !s_y || !z || !idx || !d2 || !params || !out || n < 1 || M < 0 || k < 1) return CMX_ERR_BAD_ARG;
+    if (k > CMX_MAX_K) return CMX_ERR_K_TOO_LARGE;
+    if (model < CMX_VARIOGRAM_LINEAR || model > CMX_VARIOGRAM_EXPONENTIAL) return CMX_ERR_UNSUPPORTED;
+    if (metric != CMX_METRIC_EUCLIDEAN && metric != CMX_METRIC_GEOGRAPHIC) return CMX_ERR_UNSUPPORTED;
+    return solve_table<V>(s_x, s_y, z, idx, d2, M, metric, k, model, params, exact_values, out_scale, out_shift, out,
+                          sigmasq, n_singular, static_cast<cudaStream_t>(stream));
+}
+
 template <typename V>
 int ok_entry(const double* s_x, const double* s_y, const V* z, int64_t n, const double* t_x, int64_t n_x,
              const double* t_y, int64_t n_y, int grid, int metric, int k, int model, const double* params,
@@ -426,7 +480,7 @@ int ok_entry(const double* s_x, const double* s_y, const V* z, int64_t n, const 
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!s_x || !s_y || !z || !t_x || !t_y || !params || !out) return CMX_ERR_BAD_ARG;
     if (model < CMX_VARIOGRAM_LINEAR || model > CMX_VARIOGRAM_EXPONENTIAL) return CMX_ERR_UNSUPPORTED;
-    if (metric != CMX_METRIC_EUCLIDEAN) return CMX_ERR_UNSUPPORTED;  // geographic: chord kNN not built yet
+    if (metric != CMX_METRIC_EUCLIDEAN) return CMX_ERR_UNSUPPORTED;  // geographic: cmx_knn3 + cmx_ok_solve_*
     if (k < 1) return CMX_ERR_BAD_ARG;
     if (k > CMX_MAX_K) return CMX_ERR_K_TOO_LARGE;
     if (n_x < 0 || n_y < 0) return CMX_ERR_BAD_ARG;
@@ -457,28 +511,8 @@ int ok_entry(const double* s_x, const double* s_y, const V* z, int64_t n, const 
     if (rc != CMX_OK) return rc;
     if (M == 0) return CMX_OK;
 
-    OkArgs a;
-    a.s_x = s_x;
-    a.s_y = s_y;
-    a.z = z;
-    a.z_is_f32 = sizeof(V) == 4;
-    a.idx = idx_tab;
-    a.d2 = d2_tab;
-    a.M = M;
-    a.k = k;
-    a.model = model;
-    a.p0 = params[0];
-    a.p1 = params[1];
-    a.p2 = params[2];
-    a.exact_values = exact_values;
-    a.out_scale = out_scale;
-    a.out_shift = out_shift;
-    a.out = out;
-    a.sigmasq = sigmasq;
-    a.n_singular = n_singular;
-    if (k <= 32) return launch_ok<1, V>(a, stream);
-    if (k <= 64) return launch_ok_team<2, V>(a, stream);
-    return launch_ok_team<4, V>(a, stream);
+    return solve_table<V>(s_x, s_y, z, idx_tab, d2_tab, M, CMX_METRIC_EUCLIDEAN, k, model, params, exact_values,
+                          out_scale, out_shift, out, sigmasq, n_singular, stream);
 }
 
 }  // namespace
@@ -497,6 +531,20 @@ int cmx_ok_mw_f64(const double* s_x, const double* s_y, const double* z, int64_t
                   int32_t* n_singular, void* ws, size_t ws_bytes, void* stream) {
     return cmx::ok_entry<double>(s_x, s_y, z, n, t_x, n_x, t_y, n_y, grid, metric, k, model, params, exact_values,
                                  out_scale, out_shift, out, sigmasq, n_singular, ws, ws_bytes, stream);
+}
+int cmx_ok_solve_f64(const double* s_x, const double* s_y, const double* z, int64_t n, const int32_t* idx,
+                     const double* d2, int64_t M, int metric, int k, int model, const double params[3],
+                     int exact_values, double out_scale, double out_shift, double* out, double* sigmasq,
+                     int32_t* n_singular, void* stream) {
+    return cmx::solve_entry<double>(s_x, s_y, z, n, idx, d2, M, metric, k, model, params, exact_values, out_scale,
+                                    out_shift, out, sigmasq, n_singular, stream);
+}
+int cmx_ok_solve_f32(const double* s_x, const double* s_y, const float* z, int64_t n, const int32_t* idx,
+                     const double* d2, int64_t M, int metric, int k, int model, const double params[3],
+                     int exact_values, double out_scale, double out_shift, float* out, float* sigmasq,
+                     int32_t* n_singular, void* stream) {
+    return cmx::solve_entry<float>(s_x, s_y, z, n, idx, d2, M, metric, k, model, params, exact_values, out_scale,
+                                   out_shift, out, sigmasq, n_singular, stream);
 }
 int cmx_ok_mw_f32(const double* s_x, const double* s_y, const float* z, int64_t n, const double* t_x, int64_t n_x,
                   const double* t_y, int64_t n_y, int grid, int metric, int k, int model, const double params[3],

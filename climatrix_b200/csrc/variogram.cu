@@ -21,21 +21,6 @@ namespace {
 constexpr int VT = 256;        // tile edge == threads per CTA
 constexpr int MAX_LAGS = 64;
 
-__device__ __forceinline__ double deg2rad(double v) { return v * 3.141592653589793 / 180.0; }
-
-// pykrige core.great_circle_distance (Vincenty atan2 form), degrees in, degrees out
-__device__ __forceinline__ double great_circle_deg(double lon1, double lat1, double lon2, double lat2) {
-    const double la1 = deg2rad(lat1), la2 = deg2rad(lat2);
-    const double dlon = deg2rad(lon1 - lon2);
-    double s1, c1, s2, c2, sd, cd;
-    sincos(la1, &s1, &c1);
-    sincos(la2, &s2, &c2);
-    sincos(dlon, &sd, &cd);
-    const double a = c2 * sd;
-    const double b = c1 * s2 - s1 * c2 * cd;
-    return 180.0 / 3.141592653589793 * atan2(sqrt(a * a + b * b), s1 * s2 + c1 * c2 * cd);
-}
-
 template <int METRIC>
 __device__ __forceinline__ double pair_key(double xi, double yi, double xj, double yj) {
     // euclidean: squared distance (sqrt is monotone, taken once at the end); geographic: the distance

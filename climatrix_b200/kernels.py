@@ -23,6 +23,8 @@ __all__ = [
     "idw_apply",
     "empirical_variogram",
     "ok_moving_window",
+    "knn3",
+    "ok_solve",
     "launch_count",
     "reset_launch_count",
 ]
@@ -330,6 +332,49 @@ def ok_moving_window(s_x, s_y, z, t_x, t_y, grid: bool, *, k: int, variogram_mod
                 _lib.METRIC_GEOGRAPHIC if geographic else _lib.METRIC_EUCLIDEAN, k, model, p, int(exact_values),
                 float(out_scale), float(out_shift), _ptr(out), _ptr(sig), _ptr(nsing), _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "cmx_ok_mw")
+    if return_sigmasq:
+        return out, sig, nsing
+    return out, nsing
+
+
+def knn3(s_xyz, t_xyz, k: int):
+    """Exact 3-D k-NN (geographic kriging: chords between unit vectors).  ``s_xyz`` (N, 3), ``t_xyz`` (M, 3).
+    Returns ``(d2 (M, k) float64 squared chord lengths, idx (M, k) int32)``, rows ascending by (d2, index)."""
+    lib = _lib.load()
+    dev = _require_cuda(s_xyz.device if isinstance(s_xyz, torch.Tensor) else None)
+    s = [_as_f64(np.asarray(s_xyz)[:, i] if not isinstance(s_xyz, torch.Tensor) else s_xyz[:, i], dev) for i in range(3)]
+    t = [_as_f64(np.asarray(t_xyz)[:, i] if not isinstance(t_xyz, torch.Tensor) else t_xyz[:, i], dev) for i in range(3)]
+    n, m, k = s[0].numel(), t[0].numel(), int(k)
+    with torch.cuda.device(dev):
+        idx = torch.empty((m, k), dtype=torch.int32, device=dev)
+        d2 = torch.empty((m, k), dtype=torch.float64, device=dev)
+        rc = lib.cmx_knn3(_ptr(s[0]), _ptr(s[1]), _ptr(s[2]), n, _ptr(t[0]), _ptr(t[1]), _ptr(t[2]), m, k,
+                          _ptr(idx), _ptr(d2), _stream())
+    _lib.check(rc, "cmx_knn3")
+    return d2, idx
+
+
+def ok_solve(s_x, s_y, z, idx: torch.Tensor, d2: torch.Tensor, *, variogram_model: str, params,
+             geographic: bool = False, exact_values: bool = True, out_scale: float = 1.0, out_shift: float = 0.0,
+             dtype: torch.dtype = torch.float64, return_sigmasq: bool = False):
+    """K4 on an existing neighbour table (``idx``, squared distances ``d2``): one kriging window per row."""
+    lib = _lib.load()
+    dev = _require_cuda(idx.device)
+    s_x, s_y = _as_f64(s_x, dev), _as_f64(s_y, dev)
+    if not isinstance(z, torch.Tensor):
+        z = torch.as_tensor(np.ascontiguousarray(z))
+    z = z.to(device=dev, dtype=dtype).contiguous()
+    m, k = idx.shape
+    p = (ctypes.c_double * 3)(*[float(v) for v in list(params) + [0.0] * (3 - len(params))])
+    with torch.cuda.device(dev):
+        out = torch.empty(m, dtype=dtype, device=dev)
+        sig = torch.empty(m, dtype=dtype, device=dev) if return_sigmasq else None
+        nsing = torch.zeros(1, dtype=torch.int32, device=dev)
+        fn = lib.cmx_ok_solve_f64 if dtype == torch.float64 else lib.cmx_ok_solve_f32
+        rc = fn(_ptr(s_x), _ptr(s_y), _ptr(z), s_x.numel(), _ptr(idx.contiguous()), _ptr(d2.contiguous()), m,
+                _lib.METRIC_GEOGRAPHIC if geographic else _lib.METRIC_EUCLIDEAN, k, _lib.VARIOGRAM_MODELS[variogram_model],
+                p, int(exact_values), float(out_scale), float(out_shift), _ptr(out), _ptr(sig), _ptr(nsing), _stream())
+    _lib.check(rc, "cmx_ok_solve")
     if return_sigmasq:
         return out, sig, nsing
     return out, nsing

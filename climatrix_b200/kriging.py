@@ -233,12 +233,29 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
                 raise ValueError("xpoints and ypoints must have same dimensions when treated as listing discrete points.")
             tdtype = torch.float64 if self.dtype == "float64" else torch.float32
 
-            if self.n_closest_points is not None:
-                if geographic:
-                    raise NotImplementedError(
-                        "moving-window kriging with coordinates_type='geographic' (3-D chord neighbour search) "
-                        "is not built yet; use coordinates_type='euclidean' or the global mode"
-                    )
+            if self.n_closest_points is not None and geographic:
+                # pykrige: neighbours by chord length between unit vectors, then great-circle distances
+                # (SURVEY.md Appendix A.2 steps 2 and 5); the unit vectors are built on the host with the
+                # same NumPy expressions, K1b finds the neighbours, K4 solves with the great-circle metric.
+                def unit(lon_deg, lat_deg):
+                    lon_r, lat_r = lon_deg * np.pi / 180.0, lat_deg * np.pi / 180.0
+                    return np.stack((np.cos(lon_r) * np.cos(lat_r), np.sin(lon_r) * np.cos(lat_r), np.sin(lat_r)), axis=1)
+
+                if sparse_target:
+                    gx, gy = xpts, ypts
+                else:
+                    gxm, gym = np.meshgrid(xpts, ypts)
+                    gx, gy = gxm.ravel(), gym.ravel()
+                d2, idx = kernels.knn3(unit(x_adj, y_adj), unit(gx, gy), self.n_closest_points)
+                out, nsing = kernels.ok_solve(
+                    xs, ys, zs.to(tdtype), idx, d2, variogram_model=self.variogram_model, params=params,
+                    geographic=True, exact_values=True, out_scale=float(v_std), out_shift=float(v_mean), dtype=tdtype,
+                )
+                n_sing = int(nsing.item())
+                if n_sing:
+                    raise np.linalg.LinAlgError(f"{n_sing} kriging windows are singular")
+                values = out.cpu().numpy()
+            elif self.n_closest_points is not None:
                 # for a grid, anisotropy acts on the axes separately (angle 0): adjust them once
                 if sparse_target:
                     tx, ty = _anisotropy(xpts, ypts, xc, yc, scaling)

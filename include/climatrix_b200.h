@@ -19,6 +19,7 @@
  *                         reached from src/climatrix/reconstruct/kriging.py:215-224
  *   cmx_ok_mw_f64/_f32 <- pykrige OrdinaryKriging.execute(backend="loop",
  *                         n_closest_points=k), call site kriging.py:236-241
+ *   cmx_knn3, cmx_ok_solve_* <- the same call with coordinates_type="geographic"
  *
  * Conventions
  *  - All data pointers are DEVICE pointers owned by the caller; nothing is
@@ -172,6 +173,30 @@ int cmx_ok_mw_f32(const double* s_x, const double* s_y, const float* z, int64_t 
                   double out_scale, double out_shift,
                   float* out, float* sigmasq_out, int32_t* n_singular,
                   void* workspace, size_t workspace_bytes, void* stream);
+/*
+ * Geographic mode (pykrige coordinates_type="geographic"), in two calls:
+ *  cmx_knn3       exact 3-D k-NN between unit vectors (cKDTree on (cos lon cos lat, sin lon cos lat,
+ *                 sin lat)); explicit target points; writes sample
+ *                 indices and SQUARED chord lengths, rows ascending by (d2, index).  No workspace.
+ *  cmx_ok_solve_* K4 on an existing neighbour table.  metric = CMX_METRIC_GEOGRAPHIC: d2 holds squared
+ *                 chords (converted by 180 - 360/pi acos(chord/2)), s_x = lon, s_y = lat in degrees and
+ *                 the window matrix uses the great-circle (Vincenty atan2) distance;
+ *                 CMX_METRIC_EUCLIDEAN: d2 holds squared Euclidean distances in the (s_x, s_y) frame.
+ */
+int cmx_knn3(const double* s_x, const double* s_y, const double* s_z, int64_t n_samples,
+             const double* t_x, const double* t_y, const double* t_z, int64_t n_targets,
+             int k, int32_t* idx_out, double* d2_out, void* stream);
+int cmx_ok_solve_f64(const double* s_x, const double* s_y, const double* z, int64_t n_samples,
+                     const int32_t* idx, const double* d2, int64_t n_targets, int metric, int k,
+                     int variogram_model, const double params[3], int exact_values,
+                     double out_scale, double out_shift,
+                     double* out, double* sigmasq_out, int32_t* n_singular, void* stream);
+int cmx_ok_solve_f32(const double* s_x, const double* s_y, const float* z, int64_t n_samples,
+                     const int32_t* idx, const double* d2, int64_t n_targets, int metric, int k,
+                     int variogram_model, const double params[3], int exact_values,
+                     double out_scale, double out_shift,
+                     float* out, float* sigmasq_out, int32_t* n_singular, void* stream);
+
 /* total scratch for cmx_ok_mw_* (includes the kNN scratch) */
 size_t cmx_ok_workspace_bytes(int k, int64_t n_targets);
 

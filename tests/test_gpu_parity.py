@@ -319,7 +319,7 @@ def test_moving_window_kernel_matches_restated_pykrige(model, k):
     assert np.max(np.abs(sig.cpu().numpy().reshape(30, 40) - sr)) <= OK_RTOL * max(np.max(np.abs(sr)), 1e-30)
 
 
-@pytest.mark.parametrize("name", [n for n in golden_names("ok_mw_") if "geographic" not in n])
+@pytest.mark.parametrize("name", golden_names("ok_mw_"))
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
 def test_ok_reconstructor_moving_window_matches_golden(name, dtype):
     g = load_golden(name)
@@ -399,10 +399,27 @@ def test_kriging_properties():
     assert int(nsing) == 1 and np.isnan(o[0]) and np.isfinite(o[1])
     out, nsing = K.ok_moving_window(x, y, z, tx, ty, False, k=8, variogram_model="spherical", params=[1.0, 0.5, 0.05])
     assert int(nsing) == 0 and np.isfinite(out.cpu().numpy()).all()
-    # geographic moving window is not built yet and says so
-    with pytest.raises(NotImplementedError):
-        cm.OrdinaryKrigingReconstructor(src, cm.Domain.from_lat_lon(la, lo, kind="sparse"), coordinates_type="geographic",
-                                        n_closest_points=8).reconstruct()
+
+
+def test_knn3_matches_ckdtree_on_unit_vectors():
+    """Geographic mode: 3-D chord neighbours (pykrige builds a cKDTree on unit vectors)."""
+    from scipy.spatial import cKDTree
+
+    rng = np.random.default_rng(17)
+
+    def unit(lon, lat):
+        lo, la = np.deg2rad(lon), np.deg2rad(lat)
+        return np.stack((np.cos(lo) * np.cos(la), np.sin(lo) * np.cos(la), np.sin(la)), axis=1)
+
+    s = unit(rng.uniform(-180, 180, 3000), rng.uniform(-90, 90, 3000))
+    t = unit(rng.uniform(-180, 180, 2000), rng.uniform(-90, 90, 2000))
+    for k in (1, 16, 40, 100):
+        d2, idx = K.knn3(s, t, k)
+        d0, i0 = cKDTree(s).query(t, k=k)
+        if k == 1:
+            d0, i0 = d0[:, None], i0[:, None]
+        np.testing.assert_array_equal(idx.cpu().numpy(), i0)
+        np.testing.assert_array_equal(np.sqrt(d2.cpu().numpy()), d0)
 
 
 def test_launch_counter_counts_kernels():

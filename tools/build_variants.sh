@@ -6,7 +6,7 @@ mkdir -p build/variants
 for spec in "$@"; do
   name="${spec%%:*}"; flags="${spec#*:}"
   objs=""
-  for f in capi knn idw variogram kriging; do
+  for f in capi knn knn3 idw variogram kriging; do
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC $flags -Xptxas -v -c climatrix_b200/csrc/$f.cu -o build/variants/${name}_$f.o 2> build/variants/${name}_$f.log
     objs="$objs build/variants/${name}_$f.o"
   done
