@@ -567,12 +567,16 @@ __global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __g
                     }
                 }
                 // ---- groups that may hold a neighbour: the warp re-examines them, one sample per lane ----
+                bool anyq = false;
+#pragma unroll
+                for (int q = 0; q < QPT; ++q) anyq |= mn[q] < thr[q];
+                if (!__any_sync(kFull, anyq)) continue;  // the common case for large N: one vote per group
+                const float* cs = comp + ((g0 + lane) >> 2) * 12 + (lane & 3);
+                const float xa = cs[0], xb = cs[4], xs = cs[8];
 #pragma unroll
                 for (int q = 0; q < QPT; ++q) {
                     unsigned hit = __ballot_sync(kFull, mn[q] < thr[q]);
                     if (hit) {
-                        const float* cs = comp + ((g0 + lane) >> 2) * 12 + (lane & 3);
-                        const float xa = cs[0], xb = cs[4], xs = cs[8];
                         do {
                             const int L = __ffs(hit) - 1;
                             hit &= hit - 1;
