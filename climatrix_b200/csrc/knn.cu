@@ -39,9 +39,6 @@ constexpr int THREADS = WARPS * 32;
 #ifndef CMX_CTAS
 #define CMX_CTAS 5
 #endif
-#ifndef CMX_QPT
-#define CMX_QPT 8
-#endif
 #ifndef CMX_UNROLL
 #define CMX_UNROLL 2
 #endif
@@ -53,8 +50,12 @@ constexpr int GRP = 32;              // samples per filter group (= one per lane
 constexpr int CAP = 64;              // candidate slots per target
 constexpr int FLUSH_AT = CAP - GRP;  // re-rank a target once it holds more than this
 constexpr int MAX_CTAS_PER_SM = CMX_CTAS;
-constexpr int MAX_QPT = 8;
-constexpr int MAX_TQ = WARPS * MAX_QPT * 32;
+// resident CTAs per SM: the 16-targets-per-thread variant (large N) needs 128 registers
+constexpr int ctas_per_sm(int qpt) { return qpt >= 16 ? 4 : MAX_CTAS_PER_SM; }
+// target slots of scratch per SM, enough for either variant
+constexpr int SLOTS_PER_SM = (ctas_per_sm(16) * WARPS * 16 * 32 > MAX_CTAS_PER_SM * WARPS * 8 * 32)
+                                 ? ctas_per_sm(16) * WARPS * 16 * 32
+                                 : MAX_CTAS_PER_SM * WARPS * 8 * 32;
 constexpr size_t WARP_SMEM = 2 * 2 * SS * sizeof(double) + 3 * SS * sizeof(float) + 64;  // raw x2, comp, mbarriers
 #ifndef CMX_GMAX
 #define CMX_GMAX 2048
@@ -394,7 +395,7 @@ __device__ __forceinline__ float min3f(float a, float b, float c) {
 // issued by lane 0, completion on the warp's two mbarriers), re-centres them on its tile and
 // filters.  There is no CTA-wide barrier anywhere in the kernel.
 template <int E, int QPT, bool COLSHARE>
-__global__ void __launch_bounds__(THREADS, MAX_CTAS_PER_SM) knn_kernel(const __grid_constant__ KnnArgs a) {
+__global__ void __launch_bounds__(THREADS, ctas_per_sm(QPT)) knn_kernel(const __grid_constant__ KnnArgs a) {
     constexpr int TQW = QPT * 32;  // targets per warp tile
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x;
@@ -669,9 +670,9 @@ constexpr size_t SEED_BYTES = (512 + (size_t)SAT_LD * SAT_LD * sizeof(int) + 255
 
 size_t knn_workspace_bytes(int k) {
     if (k < 1 || k > CMX_MAX_K) return 0;
-    const size_t ctas = (size_t)sm_count() * MAX_CTAS_PER_SM;
+    const size_t nslots = (size_t)sm_count() * SLOTS_PER_SM;
     const size_t kp = 32 * (size_t)list_slots(k);
-    return ctas * MAX_TQ * (CAP * sizeof(unsigned) + kp * (sizeof(double) + sizeof(int))) + SEED_BYTES + 512;
+    return nslots * (CAP * sizeof(unsigned) + kp * (sizeof(double) + sizeof(int))) + SEED_BYTES + 512;
 }
 
 int run_knn(const KnnJob& job, cudaStream_t stream) {
@@ -692,10 +693,7 @@ int run_knn(const KnnJob& job, cudaStream_t stream) {
     args.M = M;
     args.aligned = ((reinterpret_cast<uintptr_t>(job.s_a) | reinterpret_cast<uintptr_t>(job.s_b)) & 15u) == 0;
     const int sms = sm_count();
-    const int slots = sms * MAX_CTAS_PER_SM;
 
-    // Large tiles (8 targets per thread) amortise the shared-memory loads best; fall back to
-    // 2 per thread when that would leave SMs idle.
     auto tiles_for = [&](int qpt, int& tiles_c) -> long long {  // warp tiles: qpt rows x 32 columns
         if (job.grid) {
             tiles_c = (int)((job.n_b + 31) / 32);
@@ -704,18 +702,26 @@ int run_knn(const KnnJob& job, cudaStream_t stream) {
         tiles_c = 1;
         return (M + qpt * 32 - 1) / (qpt * 32);
     };
-    // 8 targets per thread amortise the shared-memory loads best (large problems); small problems are
-    // latency bound (per-target re-ranks are serial inside a warp), so they get fewer targets per warp.
-    int tiles_c8 = 1, tiles_c2 = 1, tiles_c1 = 1;
-    const long long t8 = tiles_for(CMX_QPT, tiles_c8);
-    const long long t2 = tiles_for(2, tiles_c2);
-    const long long t1 = tiles_for(1, tiles_c1);
-    const long long total_warps = (long long)slots * WARPS;
-    const int qpt = t8 >= 2 * total_warps ? CMX_QPT : (t2 >= total_warps ? 2 : 1);
-    const long long tiles = qpt == CMX_QPT ? t8 : (qpt == 2 ? t2 : t1);
+    // Targets per thread: 16 for large sample sets (fewest shared-memory loads per pair; throughput bound),
+    // 8 by default, 2 or 1 for small problems (latency bound: per-target re-ranks are serial inside a warp,
+    // so they are spread over more warps).
+    int tc16 = 1, tc8 = 1, tc2 = 1, tc1 = 1;
+    const long long t16 = tiles_for(16, tc16), t8 = tiles_for(8, tc8), t2 = tiles_for(2, tc2), t1 = tiles_for(1, tc1);
+    const long long warps16 = (long long)sms * ctas_per_sm(16) * WARPS, warps8 = (long long)sms * ctas_per_sm(8) * WARPS;
+    int qpt;
+    long long tiles;
+    if (job.n >= 262144 && t16 >= 2 * warps16) {
+        qpt = 16, tiles = t16, args.tiles_c = tc16;
+    } else if (t8 >= 2 * warps8) {
+        qpt = 8, tiles = t8, args.tiles_c = tc8;
+    } else if (t2 >= warps8) {
+        qpt = 2, tiles = t2, args.tiles_c = tc2;
+    } else {
+        qpt = 1, tiles = t1, args.tiles_c = tc1;
+    }
     if (tiles > 0x7fffffffLL) return CMX_ERR_TOO_MANY;
-    args.tiles_c = qpt == CMX_QPT ? tiles_c8 : (qpt == 2 ? tiles_c2 : tiles_c1);
     args.num_tiles = (int)tiles;
+    const int slots = sms * ctas_per_sm(qpt);
     const long long ctas_needed = (tiles + WARPS - 1) / WARPS;
     const int ctas = (int)(ctas_needed < slots ? ctas_needed : slots);
 
@@ -727,7 +733,7 @@ int run_knn(const KnnJob& job, cudaStream_t stream) {
     double* bbox = reinterpret_cast<double*>(ws + 128);
     int* sat = reinterpret_cast<int*>(ws + 512);
     ws += SEED_BYTES;
-    const size_t nslots = (size_t)slots * MAX_TQ;
+    const size_t nslots = (size_t)sms * SLOTS_PER_SM;
     args.list_d = reinterpret_cast<double*>(ws);
     args.cand = reinterpret_cast<unsigned*>(ws + nslots * kp * sizeof(double));
     args.list_i = reinterpret_cast<int*>(ws + nslots * kp * sizeof(double) + nslots * CAP * sizeof(unsigned));
@@ -748,19 +754,17 @@ int run_knn(const KnnJob& job, cudaStream_t stream) {
     if (rc != CMX_OK) return rc;
 
     const int e = list_slots(job.k);
-    if (qpt == CMX_QPT) {
-        if (e == 1) return launch<1, CMX_QPT>(args, ctas, stream);
-        if (e == 2) return launch<2, CMX_QPT>(args, ctas, stream);
-        return launch<4, CMX_QPT>(args, ctas, stream);
-    }
-    if (qpt == 2) {
-        if (e == 1) return launch<1, 2>(args, ctas, stream);
-        if (e == 2) return launch<2, 2>(args, ctas, stream);
-        return launch<4, 2>(args, ctas, stream);
-    }
-    if (e == 1) return launch<1, 1>(args, ctas, stream);
-    if (e == 2) return launch<2, 1>(args, ctas, stream);
-    return launch<4, 1>(args, ctas, stream);
+#define CMX_DISPATCH(Q)                                            \
+    do {                                                           \
+        if (e == 1) return launch<1, Q>(args, ctas, stream);       \
+        if (e == 2) return launch<2, Q>(args, ctas, stream);       \
+        return launch<4, Q>(args, ctas, stream);                   \
+    } while (0)
+    if (qpt == 16) CMX_DISPATCH(16);
+    if (qpt == 8) CMX_DISPATCH(8);
+    if (qpt == 2) CMX_DISPATCH(2);
+    CMX_DISPATCH(1);
+#undef CMX_DISPATCH
 }
 
 }  // namespace cmx
