@@ -27,8 +27,8 @@ SIGNATURES = {
     "cmx_idw_workspace_bytes": (c_size_t, [c_int, c_i64, c_i64]),
     "cmx_idw_f64": (c_int, [_P, _P, c_i64, _P, c_i64, c_int, _P, c_i64, _P, c_i64, c_int, c_int, c_int, c_double, _P, _P, _P, _P, c_size_t, _P]),
     "cmx_idw_f32": (c_int, [_P, _P, c_i64, _P, c_i64, c_int, _P, c_i64, _P, c_i64, c_int, c_int, c_int, c_double, _P, _P, _P, _P, c_size_t, _P]),
-    "cmx_idw_apply_f64": (c_int, [_P, _P, c_i64, c_int, _P, c_i64, c_i64, c_int, c_int, c_int, c_double, _P, _P]),
-    "cmx_idw_apply_f32": (c_int, [_P, _P, c_i64, c_int, _P, c_i64, c_i64, c_int, c_int, c_int, c_double, _P, _P]),
+    "cmx_idw_apply_f64": (c_int, [_P, _P, c_i64, c_int, _P, c_i64, c_i64, c_int, c_int, c_int, c_double, _P, _P, _P]),
+    "cmx_idw_apply_f32": (c_int, [_P, _P, c_i64, c_int, _P, c_i64, c_i64, c_int, c_int, c_int, c_double, _P, _P, _P]),
     "cmx_variogram_minmax": (c_int, [_P, _P, c_i64, c_int, _P, _P]),
     "cmx_variogram_bins": (c_int, [_P, _P, _P, c_i64, c_int, c_int, _P, _P, _P, _P, _P]),
     "cmx_ok_workspace_bytes": (c_size_t, [c_int, c_i64]),

@@ -250,15 +250,16 @@ int idw_entry(const double* s_lat, const double* s_lon, int64_t n, const V* vals
 
 template <typename V>
 int apply_entry(const int32_t* idx, const double* dist, int64_t M, int k_table, const V* vals, int64_t n,
-                int64_t n_batch, int layout, int k_use, int k_min, double power, V* out, void* stream_) {
+                int64_t n_batch, int layout, int k_use, int k_min, double power, V* out, int32_t* flag_scratch,
+                void* stream_) {
     if (!idx || !dist || !vals || !out) return CMX_ERR_BAD_ARG;
     if (M < 0 || n_batch < 1 || k_use < 1 || k_use > k_table || k_min < 1) return CMX_ERR_BAD_ARG;
     if (k_use > CMX_MAX_K) return CMX_ERR_K_TOO_LARGE;
     if (layout != CMX_LAYOUT_BATCH_MAJOR && layout != CMX_LAYOUT_SAMPLE_MAJOR) return CMX_ERR_BAD_ARG;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    // no scratch here: the batched kernel then tests every value for finiteness itself
-    return idw_from_table<V>(idx, dist, 0, M, k_table, k_use, k_min, power, vals, n, n_batch, layout, out, nullptr,
-                             stream);
+    // without scratch the batched kernel tests every value for finiteness itself
+    return idw_from_table<V>(idx, dist, 0, M, k_table, k_use, k_min, power, vals, n, n_batch, layout, out,
+                             flag_scratch, stream);
 }
 
 }  // namespace
@@ -286,12 +287,16 @@ int cmx_idw_f32(const double* s_lat, const double* s_lon, int64_t n, const float
                                  power, out, idx_out, dist_out, ws, ws_bytes, stream);
 }
 int cmx_idw_apply_f64(const int32_t* idx, const double* dist, int64_t M, int k_table, const double* vals, int64_t n,
-                      int64_t n_batch, int layout, int k_use, int k_min, double power, double* out, void* stream) {
-    return cmx::apply_entry<double>(idx, dist, M, k_table, vals, n, n_batch, layout, k_use, k_min, power, out, stream);
+                      int64_t n_batch, int layout, int k_use, int k_min, double power, double* out,
+                      int32_t* flag_scratch, void* stream) {
+    return cmx::apply_entry<double>(idx, dist, M, k_table, vals, n, n_batch, layout, k_use, k_min, power, out,
+                                    flag_scratch, stream);
 }
 int cmx_idw_apply_f32(const int32_t* idx, const double* dist, int64_t M, int k_table, const float* vals, int64_t n,
-                      int64_t n_batch, int layout, int k_use, int k_min, double power, float* out, void* stream) {
-    return cmx::apply_entry<float>(idx, dist, M, k_table, vals, n, n_batch, layout, k_use, k_min, power, out, stream);
+                      int64_t n_batch, int layout, int k_use, int k_min, double power, float* out,
+                      int32_t* flag_scratch, void* stream) {
+    return cmx::apply_entry<float>(idx, dist, M, k_table, vals, n, n_batch, layout, k_use, k_min, power, out,
+                                   flag_scratch, stream);
 }
 
 }  // extern "C"

@@ -212,6 +212,19 @@ def idw(s_lat, s_lon, values, targets: Targets, *, k: int = 5, power: float = 2.
     n = s_lat.numel()
     if not isinstance(values, torch.Tensor):
         values = torch.as_tensor(np.ascontiguousarray(values))
+    if values.device.type == "cpu" and values.dim() == 2 and values.numel() >= (1 << 22) and out is None:
+        # Host-resident batch: the values are only needed by the weighting kernel, so their host->device
+        # copy runs on a side stream while the neighbour search (which needs coordinates only) computes.
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(dev)
+            with torch.cuda.stream(side):
+                vals_d = values.to(device=dev, dtype=dtype, non_blocking=True)
+            dist, idx = knn(s_lat, s_lon, targets, k)
+            main.wait_stream(side)
+            vals_d.record_stream(main)
+            res = idw_apply(idx, dist, vals_d, k=k, power=power, k_min=k_min, dtype=dtype, layout=layout, n_samples=n)
+        return (res, dist, idx) if return_neighbours else res
     values = values.to(device=dev, dtype=dtype)
     values, n_batch, layout_code = _values_layout(values, n, layout)
     if n_batch > 1 and layout_code == _lib.LAYOUT_BATCH_MAJOR:
@@ -258,11 +271,15 @@ def idw_apply(idx: torch.Tensor, dist: torch.Tensor, values, *, k: int | None = 
     if n is None:
         raise ValueError("n_samples is required for batched values")
     values, n_batch, layout_code = _values_layout(values, n, layout)
+    if n_batch > 1 and layout_code == _lib.LAYOUT_BATCH_MAJOR:
+        values = values.t().contiguous()
+        layout_code = _lib.LAYOUT_SAMPLE_MAJOR
     with torch.cuda.device(dev):
         out = torch.empty((n_batch, m) if values.dim() == 2 else (m,), dtype=dtype, device=dev)
+        flag = torch.zeros(1, dtype=torch.int32, device=dev) if n_batch > 1 else None
         fn = lib.cmx_idw_apply_f64 if dtype == torch.float64 else lib.cmx_idw_apply_f32
         rc = fn(_ptr(idx.contiguous()), _ptr(dist.contiguous()), m, k_table, _ptr(values), n, n_batch, layout_code,
-                k, int(k_min), float(power), _ptr(out), _stream())
+                k, int(k_min), float(power), _ptr(out), _ptr(flag), _stream())
     _lib.check(rc, "cmx_idw_apply")
     return out
 

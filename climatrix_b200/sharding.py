@@ -74,63 +74,25 @@ def idw_on_devices(s_lat, s_lon, values, t_lat, t_lon, grid: bool, *, k: int, po
     return np.concatenate(parts, axis=-1)
 
 
-_pinned: dict = {}
-_CHUNK_BYTES = 64 << 20
-
-
 def _to_host(t):
-    """Device -> host NumPy array (freshly owned by the caller).
+    """Device -> host NumPy array owned by the caller.
 
-    Large results are streamed in 64 MiB chunks through two pinned staging buffers: while chunk i+1
-    crosses PCIe, worker threads copy chunk i into the destination array (NumPy releases the GIL for
-    the memcpy), so the pageable-memory copy overlaps the transfer instead of following it.
+    Large results land directly in page-locked memory: a pinned tensor from torch's caching host
+    allocator receives one asynchronous DMA copy and is handed out as the NumPy array (no second,
+    pageable copy; the block returns to the allocator's cache when the array is garbage collected).
     """
-    import threading
-
     import torch
 
     nbytes = t.numel() * t.element_size()
     if nbytes < (1 << 22):
         return t.cpu().numpy()
-    t = t.contiguous()
-    flat = t.view(-1)
-    per_chunk = max(1, _CHUNK_BYTES // t.element_size())
-    key = (t.dtype, t.device.index)
-    stage = _pinned.get(key)
-    if stage is None or stage[0].numel() < per_chunk:
-        stage = [torch.empty(per_chunk, dtype=t.dtype, pin_memory=True) for _ in range(2)]
-        _pinned[key] = stage
-    out = np.empty(t.numel(), dtype=stage[0].numpy().dtype)
-    stream = torch.cuda.current_stream(t.device)
-    events = [torch.cuda.Event(), torch.cuda.Event()]
-    workers: list = [None, None]
-
-    def drain(slot, lo, hi):
-        events[slot].synchronize()
-        src = stage[slot].numpy()
-        n = hi - lo
-        half = n // 2
-        th = threading.Thread(target=np.copyto, args=(out[lo:lo + half], src[:half]))
-        th.start()
-        np.copyto(out[lo + half:hi], src[half:n])
-        th.join()
-
-    n = flat.numel()
-    i = 0
-    for lo in range(0, n, per_chunk):
-        hi = min(n, lo + per_chunk)
-        slot = i & 1
-        if workers[slot] is not None:
-            workers[slot].join()  # the staging buffer is free again
-        stage[slot][: hi - lo].copy_(flat[lo:hi], non_blocking=True)
-        events[slot].record(stream)
-        workers[slot] = threading.Thread(target=drain, args=(slot, lo, hi))
-        workers[slot].start()
-        i += 1
-    for w in workers:
-        if w is not None:
-            w.join()
-    return out.reshape(tuple(t.shape))
+    try:
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    except RuntimeError:  # page-locked memory exhausted: plain pageable copy
+        return t.cpu().numpy()
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return host.numpy()
 
 
 # --------------------------------------------------------------------------- #

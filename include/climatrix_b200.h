@@ -122,13 +122,16 @@ int cmx_idw_f32(const double* s_lat, const double* s_lon, int64_t n_samples,
 /*
  * Re-apply idw.py:163-180 to a stored neighbour table with other (k_use <= k_table,
  * power, k_min): the hyper-parameter search inner loop (optim/bayesian.py:399-405).
+ * flag_scratch: optional 4 bytes of device scratch; when given (and n_batch > 1) one pass over
+ * the values records whether any is non-finite so that the batched kernel can skip the
+ * per-value test; NULL -> every value is tested.
  */
 int cmx_idw_apply_f64(const int32_t* idx, const double* dist, int64_t n_targets, int k_table,
                       const double* vals, int64_t n_samples, int64_t n_batch, int vals_layout,
-                      int k_use, int k_min, double power, double* out, void* stream);
+                      int k_use, int k_min, double power, double* out, int32_t* flag_scratch, void* stream);
 int cmx_idw_apply_f32(const int32_t* idx, const double* dist, int64_t n_targets, int k_table,
                       const float* vals, int64_t n_samples, int64_t n_batch, int vals_layout,
-                      int k_use, int k_min, double power, float* out, void* stream);
+                      int k_use, int k_min, double power, float* out, int32_t* flag_scratch, void* stream);
 
 /* ---- empirical variogram (pykrige core._initialize_variogram_model) ---- */
 
