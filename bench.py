@@ -248,6 +248,11 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
+        # NCCL prints its version banner on stdout at communicator creation; the contract is ONE JSON line
+        # there, so stdout is pointed at stderr until the result is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     inp = make_inputs(args.workload)
     m = n_lat * n_lon
@@ -345,6 +350,9 @@ def main():
         v, sample, _ = cpu_reference(inp)
         cpu = {"value": v, "unit": "targets/s", "cores": cores, "kind": "port", "sample": sample}
 
+    if world > 1:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
     if rank == 0:
         line = {
             "metric": "target points/sec", "value": value, "unit": "targets/s", "n_gpus": world, "steps": args.steps,
@@ -354,8 +362,9 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu,
             "notes": "fp32 distance filter + exact float64 re-rank; values/output float64; NCCL all-gather of output slabs inside the step for N>1",
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        os.dup2(2, 1)
         dist.destroy_process_group()
 
 

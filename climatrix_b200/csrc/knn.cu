@@ -88,12 +88,14 @@ struct KnnArgs {
     int* list_i;    // [ctas][TQ][KP]  and their sample indices
     const SeedGrid* seed;
     const int* sat; // (GMAX+1)^2 summed-area table of sample counts (exclusive prefix)
+    int* tile_counter;  // dynamic tile scheduler (zeroed by seed_init_kernel)
 };
 
 // ------------------------------------------------------------------------------------------
 // seed grid pre-pass
 // ------------------------------------------------------------------------------------------
-__global__ void seed_init_kernel(double* bbox) {
+__global__ void seed_init_kernel(double* bbox, int* tile_counter) {
+    *tile_counter = 0;
     bbox[0] = CMX_INF;
     bbox[1] = -CMX_INF;
     bbox[2] = CMX_INF;
@@ -419,11 +421,16 @@ __global__ void __launch_bounds__(THREADS, ctas_per_sm(QPT)) knn_kernel(const __
     const long long n = a.j.n;
     const int n_st = (int)((n + SS - 1) / SS);
     const int gwarp = blockIdx.x * WARPS + warp;
-    const int nwarps = gridDim.x * WARPS;
     const long long slot0 = (long long)gwarp * TQW;  // + q*32 + lane
     const SeedGrid seed = *a.seed;
 
-    for (int tile = gwarp; tile < a.num_tiles; tile += nwarps) {
+    // warps fetch tiles from a global counter: early finishers take the remainder, which evens out the
+    // load when the tile count is not a multiple of the resident warps (multi-GPU bands)
+    for (;;) {
+        int tile = 0;
+        if (lane == 0) tile = atomicAdd(a.tile_counter, 1);
+        tile = __shfl_sync(kFull, tile, 0);
+        if (tile >= a.num_tiles) break;
         // ---------------- targets of this thread ----------------
         float Qa[QPT], Qb[COLSHARE ? 1 : QPT], thr[QPT];
         unsigned offp[(QPT + 3) / 4];  // candidate counts, 8 bits per target (<= CAP = 64)
@@ -731,6 +738,7 @@ int run_knn(const KnnJob& job, cudaStream_t stream) {
     ws = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
     SeedGrid* seed = reinterpret_cast<SeedGrid*>(ws);
     double* bbox = reinterpret_cast<double*>(ws + 128);
+    args.tile_counter = reinterpret_cast<int*>(ws + 192);
     int* sat = reinterpret_cast<int*>(ws + 512);
     ws += SEED_BYTES;
     const size_t nslots = (size_t)sms * SLOTS_PER_SM;
@@ -742,7 +750,7 @@ int run_knn(const KnnJob& job, cudaStream_t stream) {
 
     // ---- seed grid pre-pass: bbox -> geometry -> histogram -> summed-area table ----
     const int pre_blocks = (int)((job.n + 255) / 256 < (long long)sms * 8 ? (job.n + 255) / 256 : (long long)sms * 8);
-    seed_init_kernel<<<1, 1, 0, stream>>>(bbox);
+    seed_init_kernel<<<1, 1, 0, stream>>>(bbox, args.tile_counter);
     seed_bbox_kernel<<<pre_blocks, 256, 0, stream>>>(job.s_a, job.s_b, job.n, bbox);
     seed_geometry_kernel<<<1, 1, 0, stream>>>(bbox, job.n, seed);
     CMX_CUDA(cudaMemsetAsync(sat, 0, (size_t)SAT_LD * SAT_LD * sizeof(int), stream));
