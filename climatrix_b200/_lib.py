@@ -23,6 +23,7 @@ SIGNATURES = {
     "cmx_strerror": (ctypes.c_char_p, [c_int]),
     "cmx_last_cuda_error": (ctypes.c_char_p, []),
     "cmx_knn_workspace_bytes": (c_size_t, [c_int]),
+    "cmx_knn_workspace_bytes_for": (c_size_t, [c_int, c_i64, c_i64, c_i64, c_int]),
     "cmx_knn": (c_int, [_P, _P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "cmx_idw_workspace_bytes": (c_size_t, [c_int, c_i64, c_i64]),
     "cmx_idw_f64": (c_int, [_P, _P, c_i64, _P, c_i64, c_int, _P, c_i64, _P, c_i64, c_int, c_int, c_int, c_double, _P, _P, _P, _P, c_size_t, _P]),

@@ -172,6 +172,9 @@ double cmx_fp32_peak_tflops(void) {
 }
 
 size_t cmx_knn_workspace_bytes(int k) { return cmx::knn_workspace_bytes(k); }
+size_t cmx_knn_workspace_bytes_for(int k, int64_t n_samples, int64_t n_a, int64_t n_b, int target_is_grid) {
+    return cmx::knn_workspace_bytes_for(k, n_samples, n_a, n_b, target_is_grid);
+}
 
 int cmx_knn(const double* s_a, const double* s_b, int64_t n, const double* t_a, int64_t n_a, const double* t_b,
             int64_t n_b, int grid, int k, int32_t* idx_out, double* dist_out, void* ws, size_t ws_bytes,

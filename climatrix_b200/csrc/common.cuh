@@ -54,6 +54,8 @@ struct KnnJob {
     size_t workspace_bytes;
 };
 size_t knn_workspace_bytes(int k);
+// with room for the partial-list tables of the sample split the planner would choose for these sizes
+size_t knn_workspace_bytes_for(int k, long long n, long long n_a, long long n_b, int grid);
 int run_knn(const KnnJob& job, cudaStream_t stream);
 
 // ---- device helpers -----------------------------------------------------------

@@ -230,10 +230,11 @@ int idw_entry(const double* s_lat, const double* s_lon, int64_t n, const V* vals
         job.out = out;
         return run_knn(job, stream);
     }
-    // batch: neighbour table once, then the HBM-bound batched apply
+    // batch: neighbour table once, then the HBM-bound batched apply.  Workspace: [tables | kNN scratch]
     if (k < 1 || k > CMX_MAX_K) return k < 1 ? CMX_ERR_BAD_ARG : CMX_ERR_K_TOO_LARGE;
-    if (!workspace || workspace_bytes < knn_ws + cmx_idw_workspace_bytes(k, M, n_batch)) return CMX_ERR_WORKSPACE;
-    unsigned char* extra = static_cast<unsigned char*>(workspace) + knn_ws;
+    const size_t extra_bytes = (cmx_idw_workspace_bytes(k, M, n_batch) + 255) & ~size_t(255);
+    if (!workspace || workspace_bytes < knn_ws + extra_bytes + 256) return CMX_ERR_WORKSPACE;
+    unsigned char* extra = static_cast<unsigned char*>(workspace);
     extra = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(extra) + 255) & ~uintptr_t(255));
     double* d2_tab = reinterpret_cast<double*>(extra);
     int* idx_tab = reinterpret_cast<int*>(extra + (size_t)M * k * sizeof(double));
@@ -241,7 +242,8 @@ int idw_entry(const double* s_lat, const double* s_lon, int64_t n, const V* vals
     job.idw_mode = 0;
     job.d2_out = d2_tab;
     if (!job.idx_out) job.idx_out = idx_tab;
-    job.workspace_bytes = knn_ws;
+    job.workspace = extra + extra_bytes;
+    job.workspace_bytes = workspace_bytes - (size_t)((extra + extra_bytes) - static_cast<unsigned char*>(workspace));
     int rc = run_knn(job, stream);
     if (rc != CMX_OK) return rc;
     return idw_from_table<V>(job.idx_out, d2_tab, 1, M, k, k, k_min, power, vals, n, n_batch, layout, out, flag,

@@ -89,6 +89,11 @@ struct KnnArgs {
     const SeedGrid* seed;
     const int* sat; // (GMAX+1)^2 summed-area table of sample counts (exclusive prefix)
     int* tile_counter;  // dynamic tile scheduler (zeroed by seed_init_kernel)
+    // sample split: a tile is swept by nseg work units, each over 1/nseg of the samples; unit results
+    // (sorted partial lists) go to part_d/part_i [M][nseg][KP] and knn_merge_kernel finishes the job
+    int nseg;
+    double* part_d;
+    int* part_i;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -273,12 +278,58 @@ __device__ __forceinline__ bool target_coords(const KnnArgs& a, int tile, int ts
     return true;
 }
 
+// The k neighbours of target m sit sorted in registers (element e*32+lane): store the neighbour
+// table and / or evaluate the fused IDW epilogue (idw.py:163-180).  Returns the IDW value.
+template <int E>
+__device__ __forceinline__ double finish_target(const KnnArgs& a, int lane, long long m, const double (&ld)[E],
+                                                const int (&li)[E]) {
+    const int k = a.j.k;
+    double wsum = 0.0;
+    double w[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = e * 32 + lane;
+        const bool in = i < k;
+        if (in) {
+            if (a.j.idx_out) a.j.idx_out[m * k + i] = li[e];
+            if (a.j.dist_out) a.j.dist_out[m * k + i] = sqrt(ld[e]);
+            if (a.j.d2_out) a.j.d2_out[m * k + i] = ld[e];
+        }
+        w[e] = (in && a.j.idw_mode) ? idw_raw_weight(ld[e], a.j.power) : 0.0;
+        wsum += w[e];
+    }
+    if (!a.j.idw_mode) return 0.0;
+    wsum = warp_sum(wsum);  // weights /= nansum(weights)            idw.py:165
+    double num = 0.0, den = 0.0;
+    int fin = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = e * 32 + lane;
+        if (i < k) {
+            const double wn = w[e] / wsum;
+            const double v = a.j.value_is_f32 ? (double)static_cast<const float*>(a.j.vals)[li[e]]
+                                              : static_cast<const double*>(a.j.vals)[li[e]];
+            if (isfinite(v)) {  // weights[~isfinite] = 0; nansum(v*w)   idw.py:167-173
+                num += v * wn;
+                den += wn;
+                ++fin;
+            }
+        }
+    }
+    num = warp_sum(num);
+    den = warp_sum(den);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) fin += __shfl_xor_sync(kFull, fin, o);
+    if (fin < a.j.k_min || den == 0.0) return quiet_nan<double>();  // idw.py:179-180
+    return num / den;
+}
+
 // Warp-cooperative exact re-rank of one target's candidate buffer.
 // Returns the new filter threshold (mid-sweep) or the fused IDW value (final).
 template <int E>
 __device__ __noinline__ double rerank_target(const KnnArgs& a, int lane, long long slot, double ta, double tb,
                                              long long m, float qa, float qb, int cnt, bool has_list,
-                                             bool final) {
+                                             bool final, int seg) {
     constexpr int KP = 32 * E;
     double ld[E];
     int li[E];
@@ -328,45 +379,17 @@ __device__ __noinline__ double rerank_target(const KnnArgs& a, int lane, long lo
         return (double)filter_threshold(d2k, qa, qb);
     }
 
-    // ---- final: neighbour table + fused IDW epilogue (idw.py:163-180) ----
-    double wsum = 0.0;
-    double w[E];
+    if (a.nseg > 1) {  // sample split: hand the sorted partial list to the merge kernel
+        double* Pd = a.part_d + (m * a.nseg + seg) * KP;
+        int* Pi = a.part_i + (m * a.nseg + seg) * KP;
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const int i = e * 32 + lane;
-        const bool in = i < k;
-        if (in) {
-            if (a.j.idx_out) a.j.idx_out[m * k + i] = li[e];
-            if (a.j.dist_out) a.j.dist_out[m * k + i] = sqrt(ld[e]);
-            if (a.j.d2_out) a.j.d2_out[m * k + i] = ld[e];
+        for (int e = 0; e < E; ++e) {
+            Pd[e * 32 + lane] = ld[e];
+            Pi[e * 32 + lane] = li[e];
         }
-        w[e] = (in && a.j.idw_mode) ? idw_raw_weight(ld[e], a.j.power) : 0.0;
-        wsum += w[e];
+        return 0.0;
     }
-    if (!a.j.idw_mode) return 0.0;
-    wsum = warp_sum(wsum);  // weights /= nansum(weights)            idw.py:165
-    double num = 0.0, den = 0.0;
-    int fin = 0;
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const int i = e * 32 + lane;
-        if (i < k) {
-            const double wn = w[e] / wsum;
-            const double v = a.j.value_is_f32 ? (double)static_cast<const float*>(a.j.vals)[li[e]]
-                                              : static_cast<const double*>(a.j.vals)[li[e]];
-            if (isfinite(v)) {  // weights[~isfinite] = 0; nansum(v*w)   idw.py:167-173
-                num += v * wn;
-                den += wn;
-                ++fin;
-            }
-        }
-    }
-    num = warp_sum(num);
-    den = warp_sum(den);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) fin += __shfl_xor_sync(kFull, fin, o);
-    if (fin < a.j.k_min || den == 0.0) return quiet_nan<double>();  // idw.py:179-180
-    return num / den;
+    return finish_target<E>(a, lane, m, ld, li);
 }
 
 // two IEEE FMAs in one instruction (FFMA2): r = q * (x0, x1) + (c0, c1), q broadcast
@@ -427,10 +450,15 @@ __global__ void __launch_bounds__(THREADS, ctas_per_sm(QPT)) knn_kernel(const __
     // warps fetch tiles from a global counter: early finishers take the remainder, which evens out the
     // load when the tile count is not a multiple of the resident warps (multi-GPU bands)
     for (;;) {
-        int tile = 0;
-        if (lane == 0) tile = atomicAdd(a.tile_counter, 1);
-        tile = __shfl_sync(kFull, tile, 0);
-        if (tile >= a.num_tiles) break;
+        int unit = 0;
+        if (lane == 0) unit = atomicAdd(a.tile_counter, 1);
+        unit = __shfl_sync(kFull, unit, 0);
+        if (unit >= a.num_tiles * a.nseg) break;
+        const int seg = unit / a.num_tiles;  // segment-major: the units of one segment share L2-hot samples
+        const int tile = unit - seg * a.num_tiles;
+        const int st_per_seg = (n_st + a.nseg - 1) / a.nseg;
+        const int st_begin = seg * st_per_seg;
+        const int st_end = min(n_st, st_begin + st_per_seg);
         // ---------------- targets of this thread ----------------
         float Qa[QPT], Qb[COLSHARE ? 1 : QPT], thr[QPT];
         unsigned offp[(QPT + 3) / 4];  // candidate counts, 8 bits per target (<= CAP = 64)
@@ -480,7 +508,7 @@ __global__ void __launch_bounds__(THREADS, ctas_per_sm(QPT)) knn_kernel(const __
             target_coords<QPT>(a, tile, q * 32 + L, ta, tb, m);
             const float qa = __double2float_rn(__dsub_rn(ta, ca));
             const float qb = __double2float_rn(__dsub_rn(tb, cb));
-            return rerank_target<E>(a, lane, slot0 + q * 32 + L, ta, tb, m, qa, qb, cnt, has, final);
+            return rerank_target<E>(a, lane, slot0 + q * 32 + L, ta, tb, m, qa, qb, cnt, has, final, seg);
         };
 
         auto stage_is_bulk = [&](int st) -> bool {
@@ -496,10 +524,10 @@ __global__ void __launch_bounds__(THREADS, ctas_per_sm(QPT)) knn_kernel(const __
 
         // ---------------- sweep over all samples ----------------
         if (lane == 0) {
-            if (n_st > 0 && stage_is_bulk(0)) issue(0);
-            if (n_st > 1 && stage_is_bulk(1)) issue(1);
+            if (st_begin < st_end && stage_is_bulk(st_begin)) issue(st_begin);
+            if (st_begin + 1 < st_end && stage_is_bulk(st_begin + 1)) issue(st_begin + 1);
         }
-        for (int st = 0; st < n_st; ++st) {
+        for (int st = st_begin; st < st_end; ++st) {
             const long long base = (long long)st * SS;
             const int cntS = (int)((n - base) < (long long)SS ? (n - base) : (long long)SS);
             const bool bulk = stage_is_bulk(st);
@@ -535,7 +563,7 @@ __global__ void __launch_bounds__(THREADS, ctas_per_sm(QPT)) knn_kernel(const __
                 dst[8] = fmaf(fb, fb, fa * fa);
             }
             __syncwarp();  // stage complete; raw buffer b is free again
-            if (lane == 0 && st + 2 < n_st && stage_is_bulk(st + 2)) issue(st + 2);
+            if (lane == 0 && st + 2 < st_end && stage_is_bulk(st + 2)) issue(st + 2);
 
             const int cnt_pad = (cntS + GRP - 1) & ~(GRP - 1);
             const unsigned jbase = (unsigned)base;
@@ -636,7 +664,7 @@ __global__ void __launch_bounds__(THREADS, ctas_per_sm(QPT)) knn_kernel(const __
                 if (lane == L) res[q] = r;
             }
         }
-        if (a.j.idw_mode == 1) {
+        if (a.j.idw_mode == 1 && a.nseg == 1) {
 #pragma unroll
             for (int q = 0; q < QPT; ++q) {
                 if ((validm >> q) & 1u) {
@@ -653,6 +681,41 @@ __global__ void __launch_bounds__(THREADS, ctas_per_sm(QPT)) knn_kernel(const __
     }
 }
 
+// Sample split, second step: one warp per target merges the nseg sorted partial lists and finishes.
+template <int E>
+__global__ void __launch_bounds__(256) knn_merge_kernel(const __grid_constant__ KnnArgs a) {
+    constexpr int KP = 32 * E;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long m = warp0; m < a.M; m += nwarps) {
+        double ld[E];
+        int li[E];
+        const double* Pd = a.part_d + m * a.nseg * KP;
+        const int* Pi = a.part_i + m * a.nseg * KP;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            ld[e] = Pd[e * 32 + lane];
+            li[e] = Pi[e * 32 + lane];
+        }
+        for (int sg = 1; sg < a.nseg; ++sg) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {  // each 32-chunk of a sorted list is itself sorted
+                const double cd = Pd[sg * KP + e * 32 + lane];
+                const int ci = Pi[sg * KP + e * 32 + lane];
+                merge_sorted32<E>(ld, li, cd, ci, lane);
+            }
+        }
+        const double r = finish_target<E>(a, lane, m, ld, li);
+        if (a.j.idw_mode == 1 && lane == 0) {
+            if (a.j.value_is_f32)
+                static_cast<float*>(a.j.out)[m] = (float)r;
+            else
+                static_cast<double*>(a.j.out)[m] = r;
+        }
+    }
+}
+
 template <int E, int QPT>
 int launch(const KnnArgs& args, int ctas, cudaStream_t stream) {
     const size_t smem = WARPS * WARP_SMEM;
@@ -663,6 +726,12 @@ int launch(const KnnArgs& args, int ctas, cudaStream_t stream) {
     } else {
         CMX_CUDA(cudaFuncSetAttribute(knn_kernel<E, QPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         knn_kernel<E, QPT, false><<<ctas, THREADS, smem, stream>>>(args);
+    }
+    if (args.nseg > 1) {
+        const long long mblocks = (args.M * 32 + 255) / 256;
+        const long long cap = (long long)sm_count() * 16;
+        knn_merge_kernel<E><<<(unsigned)(mblocks < cap ? mblocks : cap), 256, 0, stream>>>(args);
+        note_launch();
     }
     timing_end(CMX_KERNEL_KNN, stream);
     note_launch();
@@ -675,11 +744,61 @@ constexpr size_t SEED_BYTES = (512 + (size_t)SAT_LD * SAT_LD * sizeof(int) + 255
 
 }  // namespace
 
+namespace {
+struct Plan {
+    int qpt, tiles_c, nseg;
+    long long tiles;
+};
+
+// Targets per thread: 16 for large sample sets (fewest shared-memory loads per pair; throughput bound),
+// 8 by default, 2 or 1 for small problems (latency bound: per-target re-ranks are serial inside a warp,
+// so they are spread over more warps).  When even that leaves warps idle (a multi-GPU band of a big
+// job), the sample range is split into nseg segments so that there are >= ~3 work units per warp.
+Plan make_plan(long long n, long long n_a, long long n_b, int grid) {
+    const long long M = grid ? n_a * n_b : n_a;
+    const int sms = sm_count();
+    auto tiles_for = [&](int qpt, int& tiles_c) -> long long {  // warp tiles: qpt rows x 32 columns
+        if (grid) {
+            tiles_c = (int)((n_b + 31) / 32);
+            return ((n_a + qpt - 1) / qpt) * (long long)tiles_c;
+        }
+        tiles_c = 1;
+        return (M + qpt * 32 - 1) / (qpt * 32);
+    };
+    int tc16 = 1, tc8 = 1, tc2 = 1, tc1 = 1;
+    const long long t16 = tiles_for(16, tc16), t8 = tiles_for(8, tc8), t2 = tiles_for(2, tc2), t1 = tiles_for(1, tc1);
+    const long long warps16 = (long long)sms * ctas_per_sm(16) * WARPS, warps8 = (long long)sms * ctas_per_sm(8) * WARPS;
+    Plan p;
+    p.nseg = 1;
+    if (n >= 262144 && t16 >= warps16 / 2) {
+        p.qpt = 16, p.tiles = t16, p.tiles_c = tc16;
+        const long long n_st = (n + SS - 1) / SS;
+        while (p.nseg < 8 && p.tiles * p.nseg < 3 * warps16 && n_st / (p.nseg * 2) >= 128) p.nseg *= 2;
+    } else if (t8 >= 2 * warps8) {
+        p.qpt = 8, p.tiles = t8, p.tiles_c = tc8;
+    } else if (t2 >= warps8) {
+        p.qpt = 2, p.tiles = t2, p.tiles_c = tc2;
+    } else {
+        p.qpt = 1, p.tiles = t1, p.tiles_c = tc1;
+    }
+    return p;
+}
+}  // namespace
+
 size_t knn_workspace_bytes(int k) {
     if (k < 1 || k > CMX_MAX_K) return 0;
     const size_t nslots = (size_t)sm_count() * SLOTS_PER_SM;
     const size_t kp = 32 * (size_t)list_slots(k);
     return nslots * (CAP * sizeof(unsigned) + kp * (sizeof(double) + sizeof(int))) + SEED_BYTES + 512;
+}
+
+size_t knn_workspace_bytes_for(int k, long long n, long long n_a, long long n_b, int grid) {
+    const size_t base = knn_workspace_bytes(k);
+    if (!base || n < 0 || n_a < 0 || n_b < 0) return base;
+    const Plan p = make_plan(n, n_a, n_b, grid);
+    if (p.nseg <= 1) return base;
+    const long long M = grid ? n_a * n_b : n_a;
+    return base + (size_t)M * p.nseg * 32 * list_slots(k) * (sizeof(double) + sizeof(int)) + 512;
 }
 
 int run_knn(const KnnJob& job, cudaStream_t stream) {
@@ -700,37 +819,12 @@ int run_knn(const KnnJob& job, cudaStream_t stream) {
     args.M = M;
     args.aligned = ((reinterpret_cast<uintptr_t>(job.s_a) | reinterpret_cast<uintptr_t>(job.s_b)) & 15u) == 0;
     const int sms = sm_count();
-
-    auto tiles_for = [&](int qpt, int& tiles_c) -> long long {  // warp tiles: qpt rows x 32 columns
-        if (job.grid) {
-            tiles_c = (int)((job.n_b + 31) / 32);
-            return ((job.n_a + qpt - 1) / qpt) * (long long)tiles_c;
-        }
-        tiles_c = 1;
-        return (M + qpt * 32 - 1) / (qpt * 32);
-    };
-    // Targets per thread: 16 for large sample sets (fewest shared-memory loads per pair; throughput bound),
-    // 8 by default, 2 or 1 for small problems (latency bound: per-target re-ranks are serial inside a warp,
-    // so they are spread over more warps).
-    int tc16 = 1, tc8 = 1, tc2 = 1, tc1 = 1;
-    const long long t16 = tiles_for(16, tc16), t8 = tiles_for(8, tc8), t2 = tiles_for(2, tc2), t1 = tiles_for(1, tc1);
-    const long long warps16 = (long long)sms * ctas_per_sm(16) * WARPS, warps8 = (long long)sms * ctas_per_sm(8) * WARPS;
-    int qpt;
-    long long tiles;
-    if (job.n >= 262144 && t16 >= 2 * warps16) {
-        qpt = 16, tiles = t16, args.tiles_c = tc16;
-    } else if (t8 >= 2 * warps8) {
-        qpt = 8, tiles = t8, args.tiles_c = tc8;
-    } else if (t2 >= warps8) {
-        qpt = 2, tiles = t2, args.tiles_c = tc2;
-    } else {
-        qpt = 1, tiles = t1, args.tiles_c = tc1;
-    }
-    if (tiles > 0x7fffffffLL) return CMX_ERR_TOO_MANY;
-    args.num_tiles = (int)tiles;
+    Plan plan = make_plan(job.n, job.n_a, job.n_b, job.grid);
+    if (plan.tiles > 0x7fffffffLL / 8) return CMX_ERR_TOO_MANY;
+    const int qpt = plan.qpt;
+    args.tiles_c = plan.tiles_c;
+    args.num_tiles = (int)plan.tiles;
     const int slots = sms * ctas_per_sm(qpt);
-    const long long ctas_needed = (tiles + WARPS - 1) / WARPS;
-    const int ctas = (int)(ctas_needed < slots ? ctas_needed : slots);
 
     // workspace: [seed grid | lists d | candidates | lists i]
     const size_t kp = 32 * (size_t)list_slots(job.k);
@@ -745,6 +839,18 @@ int run_knn(const KnnJob& job, cudaStream_t stream) {
     args.list_d = reinterpret_cast<double*>(ws);
     args.cand = reinterpret_cast<unsigned*>(ws + nslots * kp * sizeof(double));
     args.list_i = reinterpret_cast<int*>(ws + nslots * kp * sizeof(double) + nslots * CAP * sizeof(unsigned));
+    // optional partial-list tables of the sample split: used only if the caller's workspace has room
+    unsigned char* part = ws + nslots * (kp * (sizeof(double) + sizeof(int)) + CAP * sizeof(unsigned));
+    part = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(part) + 255) & ~uintptr_t(255));
+    const size_t part_need = (size_t)M * plan.nseg * kp * (sizeof(double) + sizeof(int));
+    unsigned char* ws_end = static_cast<unsigned char*>(job.workspace) + job.workspace_bytes;
+    if (plan.nseg > 1 && part + part_need > ws_end) plan.nseg = 1;
+    args.nseg = plan.nseg;
+    args.part_d = reinterpret_cast<double*>(part);
+    args.part_i = reinterpret_cast<int*>(part + (size_t)M * plan.nseg * kp * sizeof(double));
+    const long long units = plan.tiles * plan.nseg;
+    const long long ctas_needed = (units + WARPS - 1) / WARPS;
+    const int ctas = (int)(ctas_needed < slots ? ctas_needed : slots);
     args.seed = seed;
     args.sat = sat;
 

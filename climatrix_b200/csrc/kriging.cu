@@ -485,9 +485,10 @@ int ok_entry(const double* s_x, const double* s_y, const V* z, int64_t n, const 
     if (k > CMX_MAX_K) return CMX_ERR_K_TOO_LARGE;
     if (n_x < 0 || n_y < 0) return CMX_ERR_BAD_ARG;
     const long long M = grid ? (long long)n_x * n_y : (long long)n_x;
-    const size_t knn_ws = knn_workspace_bytes(k);
+    // workspace: [neighbour table | kNN scratch]
     if (!workspace || workspace_bytes < cmx_ok_workspace_bytes(k, M)) return CMX_ERR_WORKSPACE;
-    unsigned char* extra = static_cast<unsigned char*>(workspace) + knn_ws;
+    const size_t tab_bytes = ((size_t)M * k * (sizeof(double) + sizeof(int)) + 255) & ~size_t(255);
+    unsigned char* extra = static_cast<unsigned char*>(workspace);
     extra = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(extra) + 255) & ~uintptr_t(255));
     double* d2_tab = reinterpret_cast<double*>(extra);
     int* idx_tab = reinterpret_cast<int*>(extra + (size_t)M * k * sizeof(double));
@@ -505,8 +506,8 @@ int ok_entry(const double* s_x, const double* s_y, const V* z, int64_t n, const 
     job.k = k;
     job.idx_out = idx_tab;
     job.d2_out = d2_tab;
-    job.workspace = workspace;
-    job.workspace_bytes = knn_ws;
+    job.workspace = extra + tab_bytes;
+    job.workspace_bytes = workspace_bytes - (size_t)((extra + tab_bytes) - static_cast<unsigned char*>(workspace));
     int rc = run_knn(job, stream);
     if (rc != CMX_OK) return rc;
     if (M == 0) return CMX_OK;
@@ -522,7 +523,7 @@ extern "C" {
 
 size_t cmx_ok_workspace_bytes(int k, int64_t n_targets) {
     if (k < 1 || k > CMX_MAX_K || n_targets < 0) return 0;
-    return cmx::knn_workspace_bytes(k) + (size_t)n_targets * (size_t)k * (sizeof(double) + sizeof(int)) + 1024;
+    return cmx::knn_workspace_bytes(k) + (size_t)n_targets * (size_t)k * (sizeof(double) + sizeof(int)) + 2048;
 }
 
 int cmx_ok_mw_f64(const double* s_x, const double* s_y, const double* z, int64_t n, const double* t_x, int64_t n_x,

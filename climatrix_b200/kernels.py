@@ -142,6 +142,11 @@ def fp32_peak_tflops() -> float:
     return float(_lib.load().cmx_fp32_peak_tflops())
 
 
+def _knn_ws_bytes(lib, k: int, n: int, targets: "Targets") -> int:
+    kk = max(1, min(int(k), _lib.MAX_K))
+    return int(lib.cmx_knn_workspace_bytes_for(kk, int(n), targets.lat.numel(), targets.lon.numel(), int(targets.grid)))
+
+
 def _check_samples(s_lat, s_lon):
     if s_lat.dim() != 1 or s_lat.shape != s_lon.shape:
         raise ValueError(
@@ -165,7 +170,7 @@ def knn(s_lat, s_lon, targets: Targets, k: int, *, return_distance: bool = True)
     with torch.cuda.device(dev):
         idx = torch.empty((m, k), dtype=torch.int32, device=dev)
         dist = torch.empty((m, k), dtype=torch.float64, device=dev) if return_distance else None
-        ws = _workspace(lib.cmx_knn_workspace_bytes(max(1, min(k, _lib.MAX_K))), dev)
+        ws = _workspace(_knn_ws_bytes(lib, k, s_lat.numel(), targets), dev)
         rc = lib.cmx_knn(_ptr(s_lat), _ptr(s_lon), s_lat.numel(), _ptr(targets.lat), targets.lat.numel(),
                          _ptr(targets.lon), targets.lon.numel(), int(targets.grid), k, _ptr(idx), _ptr(dist),
                          _ptr(ws), ws.numel(), _stream())
@@ -243,7 +248,7 @@ def idw(s_lat, s_lon, values, targets: Targets, *, k: int = 5, power: float = 2.
             idx = torch.empty((m, k), dtype=torch.int32, device=dev)
             dist = torch.empty((m, k), dtype=torch.float64, device=dev)
         kk = max(1, min(k, _lib.MAX_K))
-        ws = _workspace(lib.cmx_knn_workspace_bytes(kk) + lib.cmx_idw_workspace_bytes(kk, m, n_batch), dev)
+        ws = _workspace(_knn_ws_bytes(lib, k, n, targets) + lib.cmx_idw_workspace_bytes(kk, m, n_batch) + 1024, dev)
         fn = lib.cmx_idw_f64 if dtype == torch.float64 else lib.cmx_idw_f32
         rc = fn(_ptr(s_lat), _ptr(s_lon), n, _ptr(values), n_batch, layout_code, _ptr(targets.lat),
                 targets.lat.numel(), _ptr(targets.lon), targets.lon.numel(), int(targets.grid), k, k_min,
@@ -343,7 +348,9 @@ def ok_moving_window(s_x, s_y, z, t_x, t_y, grid: bool, *, k: int, variogram_mod
         out = torch.empty(m, dtype=dtype, device=dev)
         sig = torch.empty(m, dtype=dtype, device=dev) if return_sigmasq else None
         nsing = torch.zeros(1, dtype=torch.int32, device=dev)
-        ws = _workspace(lib.cmx_ok_workspace_bytes(max(1, min(k, _lib.MAX_K)), m), dev)
+        kk = max(1, min(k, _lib.MAX_K))
+        split_extra = lib.cmx_knn_workspace_bytes_for(kk, n, t_y.numel() if grid else m, t_x.numel(), int(grid)) - lib.cmx_knn_workspace_bytes(kk)
+        ws = _workspace(lib.cmx_ok_workspace_bytes(kk, m) + split_extra + 1024, dev)
         fn = lib.cmx_ok_mw_f64 if dtype == torch.float64 else lib.cmx_ok_mw_f32
         rc = fn(_ptr(s_x), _ptr(s_y), _ptr(z), n, _ptr(t_x), t_x.numel(), _ptr(t_y), t_y.numel(), int(grid),
                 _lib.METRIC_GEOGRAPHIC if geographic else _lib.METRIC_EUCLIDEAN, k, model, p, int(exact_values),

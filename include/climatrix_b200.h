@@ -84,6 +84,12 @@ const char* cmx_last_cuda_error(void);
 
 /* Scratch bytes cmx_knn / cmx_idw_* / cmx_ok_mw_* need for `k` on the current device. */
 size_t cmx_knn_workspace_bytes(int k);
+/*
+ * Same, plus room for the partial-list tables of the sample split the library uses when the
+ * targets alone cannot fill the GPU (e.g. one rank's band of a multi-GPU job).  Passing only
+ * cmx_knn_workspace_bytes() is always valid; the split is then not used.
+ */
+size_t cmx_knn_workspace_bytes_for(int k, int64_t n_samples, int64_t n_a, int64_t n_b, int target_is_grid);
 
 /*
  * idx_out  [M][k] int32   sample indices, ascending by (dist, index)      (required)

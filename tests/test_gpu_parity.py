@@ -286,6 +286,25 @@ def test_idw_properties_at_era5_scale():
     assert rel_err(out.cpu().numpy()[sel], ref) <= 1e-12
 
 
+def test_sample_split_path_thin_band_of_a_big_job():
+    """What one rank of a multi-GPU run sees: few target rows, many samples -> the planner splits the
+    sample range into segments (partial lists + merge kernel).  Must stay bit-exact."""
+    la, lo, v, _ = _samples(400_000, 4242)
+    tl, to = np.linspace(-40, -20, 60), -180 + np.arange(3600) * 0.1
+    T = K.Targets.make(tl, to, True, DEV)
+    out, dist, idx = K.idw(la, lo, v, T, k=32, return_neighbours=True)
+    rows = np.array([0, 29, 59])
+    ref, d0, i0 = idw_oracle(sparse_points(la, lo), v, dense_points(tl[rows], to), k=32, return_neighbours=True)
+    sel = (rows[:, None] * 3600 + np.arange(3600)[None, :]).ravel()
+    np.testing.assert_array_equal(idx.cpu().numpy()[sel], i0)
+    np.testing.assert_array_equal(dist.cpu().numpy()[sel], d0)
+    assert rel_err(out.cpu().numpy()[sel], ref) <= 1e-10
+    # k = 64 (two list slots per lane) through the same path
+    dist, idx = K.knn(la, lo, T, 64)
+    d0, i0 = knn_ckdtree(sparse_points(la, lo), dense_points(tl[rows], to), 64)
+    np.testing.assert_array_equal(idx.cpu().numpy()[sel], i0)
+
+
 # ------------------------------------------------------------------------------------------
 # K3 / K4: variogram and moving-window kriging
 # ------------------------------------------------------------------------------------------
