@@ -248,6 +248,23 @@ def test_idw_apply_reuses_a_neighbour_table():
         assert rel_err(out, ref) <= 1e-12
 
 
+def test_hyperparameter_search_inner_loop_matches_per_trial_reconstructions():
+    """IDWSearch: neighbour table once at k_max, one apply per trial (optim/bayesian.py:380-425)."""
+    from climatrix_b200.hpo import IDWSearch
+
+    la, lo, v, rng = _samples(1500, 55)
+    keep = rng.random(1500) < 0.6
+    train = static_sparse(la[keep], lo[keep], v[keep])
+    val = static_sparse(la[~keep], lo[~keep], v[~keep])
+    search = IDWSearch(train, val, k_max=50)
+    for k, p, kmin in [(27, 2.87, 2), (5, 2.0, 2), (50, 0.7, 10), (1, 4.0, 1)]:
+        ref = idw_oracle(sparse_points(la[keep], lo[keep]), v[keep], sparse_points(la[~keep], lo[~keep]), k=k, power=p, k_min=kmin)
+        assert abs(search.score(k, p, kmin, "mae") - np.nanmean(np.abs(ref - v[~keep]))) <= 1e-10
+        assert abs(search.score(k, p, kmin, "rmse") - np.sqrt(np.nanmean((ref - v[~keep]) ** 2))) <= 1e-10
+    with pytest.raises(ValueError):
+        search.score(51)
+
+
 def test_reference_interface_combinations_return_the_right_kind():
     """The four sparse/dense x sparse/dense cases of test_base_interface.py:235-279 (k=5 == N)."""
     sp, de = sparse_dataset(), dense_dataset()
