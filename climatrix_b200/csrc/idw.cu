@@ -25,8 +25,8 @@ constexpr int BW_TARGETS = 32;  // targets per CTA
 template <typename V>
 __global__ void __launch_bounds__(BW_THREADS) idw_batch_kernel(
     const int* __restrict__ idx, const double* __restrict__ dd, int dist_is_squared, long long M, int k_table,
-    int k_use, int k_min, double power, const V* __restrict__ vals, long long n_batch, long long stride_t,
-    long long stride_i, const int* __restrict__ nonfinite_flag, V* __restrict__ out) {
+    int k_use, int k_min, double power, const V* __restrict__ vals, long long n_samples, long long n_batch,
+    long long stride_t, long long stride_i, const int* __restrict__ nonfinite_flag, V* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // [32][k_use] weights (double), [32][k_use] sample indices, [32] weight sums, then the transpose tile
     double* s_w = reinterpret_cast<double*>(smem_raw);
@@ -47,8 +47,11 @@ __global__ void __launch_bounds__(BW_THREADS) idw_batch_kernel(
             int id = 0;
             if (m < M) {
                 const double d = dd[m * k_table + j];
-                w = dist_is_squared ? idw_raw_weight(d, power) : idw_weight_from_dist(d, power);
                 id = idx[m * k_table + j];
+                if (id >= 0 && id < n_samples)  // the (inf, INT_MAX) sentinel of a short neighbour list carries no weight
+                    w = dist_is_squared ? idw_raw_weight(d, power) : idw_weight_from_dist(d, power);
+                else
+                    id = 0;
             }
             s_w[tl * k_use + j] = w;
             s_idx[tl * k_use + j] = id;
@@ -112,8 +115,8 @@ __global__ void __launch_bounds__(BW_THREADS) idw_batch_kernel(
 template <typename V>
 __global__ void idw_apply_single_kernel(const int* __restrict__ idx, const double* __restrict__ dd,
                                         int dist_is_squared, long long M, int k_table, int k_use, int k_min,
-                                        double power, const V* __restrict__ vals, long long stride_i,
-                                        V* __restrict__ out) {
+                                        double power, const V* __restrict__ vals, long long n_samples,
+                                        long long stride_i, V* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (m >= M) return;
@@ -125,7 +128,8 @@ __global__ void idw_apply_single_kernel(const int* __restrict__ idx, const doubl
         w[e] = 0.0;
         if (j < k_use) {
             const double d = dd[m * k_table + j];
-            w[e] = dist_is_squared ? idw_raw_weight(d, power) : idw_weight_from_dist(d, power);
+            const int id = idx[m * k_table + j];
+            if (id >= 0 && id < n_samples) w[e] = dist_is_squared ? idw_raw_weight(d, power) : idw_weight_from_dist(d, power);
         }
         wsum += w[e];
     }
@@ -135,7 +139,7 @@ __global__ void idw_apply_single_kernel(const int* __restrict__ idx, const doubl
 #pragma unroll
     for (int e = 0; e < CMX_MAX_K / 32; ++e) {
         const int j = e * 32 + lane;
-        if (j < k_use) {
+        if (j < k_use && w[e] > 0.0) {
             const double wn = w[e] / wsum;
             const double v = (double)vals[(long long)idx[m * k_table + j] * stride_i];
             if (isfinite(v)) {
@@ -172,7 +176,8 @@ int idw_from_table(const int* idx, const double* dd, int dist_is_squared, long l
         const int threads = 256;
         const long long blocks = (M * 32 + threads - 1) / threads;
         idw_apply_single_kernel<V><<<(unsigned)blocks, threads, 0, stream>>>(idx, dd, dist_is_squared, M, k_table,
-                                                                            k_use, k_min, power, vals, stride_i, out);
+                                                                            k_use, k_min, power, vals, n_samples,
+                                                                            stride_i, out);
         note_launch();
         return check_launch();
     }
@@ -189,8 +194,8 @@ int idw_from_table(const int* idx, const double* dd, int dist_is_squared, long l
         CMX_CUDA(cudaFuncSetAttribute(idw_batch_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     timing_begin(CMX_KERNEL_IDW_BATCH, stream);
     idw_batch_kernel<V><<<(unsigned)blocks, BW_THREADS, smem, stream>>>(idx, dd, dist_is_squared, M, k_table, k_use,
-                                                                       k_min, power, vals, n_batch, stride_t,
-                                                                       stride_i, flag_scratch, out);
+                                                                       k_min, power, vals, n_samples, n_batch,
+                                                                       stride_t, stride_i, flag_scratch, out);
     timing_end(CMX_KERNEL_IDW_BATCH, stream);
     note_launch();
     return check_launch();

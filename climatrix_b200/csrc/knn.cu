@@ -295,7 +295,10 @@ __device__ __forceinline__ double finish_target(const KnnArgs& a, int lane, long
             if (a.j.dist_out) a.j.dist_out[m * k + i] = sqrt(ld[e]);
             if (a.j.d2_out) a.j.d2_out[m * k + i] = ld[e];
         }
-        w[e] = (in && a.j.idw_mode) ? idw_raw_weight(ld[e], a.j.power) : 0.0;
+        // a slot still holding the (inf, INT_MAX) sentinel means fewer than k rankable samples were found
+        // (NaN coordinates): it carries no weight and its index is never dereferenced
+        const bool real = in && li[e] != INT_MAX;
+        w[e] = (real && a.j.idw_mode) ? idw_raw_weight(ld[e], a.j.power) : 0.0;
         wsum += w[e];
     }
     if (!a.j.idw_mode) return 0.0;
@@ -305,7 +308,7 @@ __device__ __forceinline__ double finish_target(const KnnArgs& a, int lane, long
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const int i = e * 32 + lane;
-        if (i < k) {
+        if (i < k && li[e] != INT_MAX) {
             const double wn = w[e] / wsum;
             const double v = a.j.value_is_f32 ? (double)static_cast<const float*>(a.j.vals)[li[e]]
                                               : static_cast<const double*>(a.j.vals)[li[e]];

@@ -33,6 +33,7 @@ struct OkArgs {
     const int* idx;     // [M][k]
     const double* d2;   // [M][k] exact squared distances (kriging frame)
     long long M;
+    long long n;  // samples (indices outside [0, n) mark a short neighbour list -> NaN)
     int k;
     int model;
     double p0, p1, p2;
@@ -102,7 +103,11 @@ __global__ void __launch_bounds__(256) ok_solve_kernel(const OkArgs a, int warps
             const int r = e * 32 + lane;
             mx[e] = my[e] = mz[e] = borig[e] = 0.0;
             if (r < k) {
-                const int id = a.idx[m * k + r];
+                int id = a.idx[m * k + r];
+                if (id < 0 || id >= a.n) {  // short neighbour list: duplicate row 0 -> singular window -> NaN
+                    id = a.idx[m * k];
+                    if (id < 0 || id >= a.n) id = 0;
+                }
                 mx[e] = a.s_x[id];
                 my[e] = a.s_y[id];
                 mz[e] = a.z_is_f32 ? (double)static_cast<const float*>(a.z)[id] : static_cast<const double*>(a.z)[id];
@@ -271,7 +276,11 @@ __global__ void __launch_bounds__(512) ok_solve_team_kernel(const OkArgs a, int 
     for (long long m = (long long)blockIdx.x * teams_per_cta + team; m < a.M; m += total_teams) {
         double mx = 0.0, my = 0.0, mz = 0.0, borig = 0.0;
         if (r < k) {
-            const int id = a.idx[m * k + r];
+            int id = a.idx[m * k + r];
+            if (id < 0 || id >= a.n) {
+                id = a.idx[m * k];
+                if (id < 0 || id >= a.n) id = 0;
+            }
             mx = a.s_x[id];
             my = a.s_y[id];
             mz = a.z_is_f32 ? (double)static_cast<const float*>(a.z)[id] : static_cast<const double*>(a.z)[id];
@@ -431,8 +440,8 @@ int launch_ok(const OkArgs& a, cudaStream_t stream) {
 
 // K4 on an existing neighbour table
 template <typename V>
-int solve_table(const double* s_x, const double* s_y, const V* z, const int* idx, const double* d2, long long M,
-                int metric, int k, int model, const double* params, int exact_values, double out_scale,
+int solve_table(const double* s_x, const double* s_y, const V* z, long long n, const int* idx, const double* d2,
+                long long M, int metric, int k, int model, const double* params, int exact_values, double out_scale,
                 double out_shift, V* out, V* sigmasq, int32_t* n_singular, cudaStream_t stream) {
     if (M == 0) return CMX_OK;
     OkArgs a;
@@ -443,6 +452,7 @@ int solve_table(const double* s_x, const double* s_y, const V* z, const int* idx
     a.idx = idx;
     a.d2 = d2;
     a.M = M;
+    a.n = n;
     a.k = k;
     a.model = model;
     a.p0 = params[0];
@@ -468,8 +478,8 @@ int solve_entry(const double* s_x, const double* s_y, const V* z, int64_t n, con
     if (k > CMX_MAX_K) return CMX_ERR_K_TOO_LARGE;
     if (model < CMX_VARIOGRAM_LINEAR || model > CMX_VARIOGRAM_EXPONENTIAL) return CMX_ERR_UNSUPPORTED;
     if (metric != CMX_METRIC_EUCLIDEAN && metric != CMX_METRIC_GEOGRAPHIC) return CMX_ERR_UNSUPPORTED;
-    return solve_table<V>(s_x, s_y, z, idx, d2, M, metric, k, model, params, exact_values, out_scale, out_shift, out,
-                          sigmasq, n_singular, static_cast<cudaStream_t>(stream));
+    return solve_table<V>(s_x, s_y, z, n, idx, d2, M, metric, k, model, params, exact_values, out_scale, out_shift,
+                          out, sigmasq, n_singular, static_cast<cudaStream_t>(stream));
 }
 
 template <typename V>
@@ -512,7 +522,7 @@ int ok_entry(const double* s_x, const double* s_y, const V* z, int64_t n, const 
     if (rc != CMX_OK) return rc;
     if (M == 0) return CMX_OK;
 
-    return solve_table<V>(s_x, s_y, z, idx_tab, d2_tab, M, CMX_METRIC_EUCLIDEAN, k, model, params, exact_values,
+    return solve_table<V>(s_x, s_y, z, n, idx_tab, d2_tab, M, CMX_METRIC_EUCLIDEAN, k, model, params, exact_values,
                           out_scale, out_shift, out, sigmasq, n_singular, stream);
 }
 

@@ -114,6 +114,48 @@ def test_knn_ties_follow_the_documented_rule():
             assert np.hypot(dense_points(tl, to)[m, 0] - la[j], dense_points(tl, to)[m, 1] - lo[j]) == kth[m]
 
 
+def test_knn_unaligned_sample_pointers_take_the_plain_load_path():
+    """8-byte aligned (not 16) sample arrays cannot be staged by TMA bulk copies: same results."""
+    la, lo, _, _ = _samples(5001, 23)
+    s_la, s_lo = torch.as_tensor(la).to(DEV)[1:], torch.as_tensor(lo).to(DEV)[1:]
+    assert s_la.data_ptr() % 16 == 8 and s_la.is_contiguous()
+    tl, to = np.linspace(-80, 80, 33), np.linspace(-170, 170, 65)
+    T = K.Targets.make(tl, to, True, DEV)
+    lib = K._lib.load()
+    import ctypes
+
+    idx = torch.empty((T.count, 12), dtype=torch.int32, device=DEV)
+    dist = torch.empty((T.count, 12), dtype=torch.float64, device=DEV)
+    ws = torch.empty(lib.cmx_knn_workspace_bytes(12), dtype=torch.uint8, device=DEV)
+    rc = lib.cmx_knn(s_la.data_ptr(), s_lo.data_ptr(), 5000, T.lat.data_ptr(), 33, T.lon.data_ptr(), 65, 1, 12,
+                     idx.data_ptr(), dist.data_ptr(), ws.data_ptr(), ws.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    d0, i0 = knn_ckdtree(sparse_points(la[1:], lo[1:]), dense_points(tl, to), 12)
+    np.testing.assert_array_equal(idx.cpu().numpy(), i0)
+    np.testing.assert_array_equal(dist.cpu().numpy(), d0)
+
+
+def test_non_finite_coordinates_do_not_crash_or_leak():
+    """NaN sample coordinates never rank; NaN target coordinates give NaN (no out-of-bounds gathers)."""
+    la, lo, v, rng = _samples(800, 29)
+    bad = rng.choice(800, 40, replace=False)
+    la_b = la.copy()
+    la_b[bad] = np.nan
+    tl, to = np.linspace(-80, 80, 21), np.linspace(-170, 170, 43)
+    out, dist, idx = K.idw(la_b, lo, v, K.Targets.make(tl, to, True, DEV), k=9, return_neighbours=True)
+    good = np.setdiff1d(np.arange(800), bad)
+    ref, d0, i0 = idw_oracle(sparse_points(la[good], lo[good]), v[good], dense_points(tl, to), k=9, return_neighbours=True)
+    np.testing.assert_array_equal(idx.cpu().numpy(), good[i0])
+    assert rel_err(out.cpu().numpy(), ref) <= 1e-12
+    tl_b = tl.copy()
+    tl_b[3] = np.nan
+    out = K.idw(la, lo, v, K.Targets.make(tl_b, to, True, DEV), k=9).cpu().numpy().reshape(21, 43)
+    assert np.isnan(out[3]).all() and np.isfinite(np.delete(out, 3, axis=0)).all()
+    vt = np.stack([v, 2 * v, v + 1], axis=1)
+    outb = K.idw(la, lo, vt, K.Targets.make(tl_b, to, True, DEV), k=9, layout="sample_major").cpu().numpy().reshape(3, 21, 43)
+    assert np.isnan(outb[:, 3]).all() and np.isfinite(np.delete(outb, 3, axis=1)).all()
+
+
 def test_knn_duplicate_coordinates_and_k_errors():
     la, lo, _, _ = _samples(150, 3)
     la[100:], lo[100:] = la[:50], lo[:50]
