@@ -22,17 +22,23 @@ constexpr int BW_WARPS = 8;
 constexpr int BW_THREADS = BW_WARPS * 32;
 constexpr int BW_TARGETS = 32;  // targets per CTA
 
+// Per (target, neighbour) the CTA keeps one 16-byte shared-memory entry {weight, byte offset of the
+// sample's value row}: the inner loop is LDS.128 (broadcast) + one 64-bit add + LDG + DFMA -- the row
+// offset (a 64-bit multiply) is computed once per target, not once per value.
+struct __align__(16) NbrEntry {
+    double w;
+    unsigned long long off;
+};
+
 template <typename V>
 __global__ void __launch_bounds__(BW_THREADS) idw_batch_kernel(
     const int* __restrict__ idx, const double* __restrict__ dd, int dist_is_squared, long long M, int k_table,
     int k_use, int k_min, double power, const V* __restrict__ vals, long long n_samples, long long n_batch,
     long long stride_t, long long stride_i, const int* __restrict__ nonfinite_flag, V* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // [32][k_use] weights (double), [32][k_use] sample indices, [32] weight sums, then the transpose tile
-    double* s_w = reinterpret_cast<double*>(smem_raw);
-    double* s_wsum = s_w + BW_TARGETS * k_use;
-    V* s_tile = reinterpret_cast<V*>(s_wsum + BW_TARGETS);  // [32][33]
-    int* s_idx = reinterpret_cast<int*>(s_tile + 32 * 33);
+    NbrEntry* s_ent = reinterpret_cast<NbrEntry*>(smem_raw);               // [32][k_use]
+    double* s_wsum = reinterpret_cast<double*>(s_ent + BW_TARGETS * k_use);  // [32]
+    V* s_tile = reinterpret_cast<V*>(s_wsum + BW_TARGETS);                   // [32][33]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long m0 = (long long)blockIdx.x * BW_TARGETS;
@@ -44,7 +50,7 @@ __global__ void __launch_bounds__(BW_THREADS) idw_batch_kernel(
         double wsum = 0.0;
         for (int j = lane; j < k_use; j += 32) {
             double w = 0.0;
-            int id = 0;
+            long long id = 0;
             if (m < M) {
                 const double d = dd[m * k_table + j];
                 id = idx[m * k_table + j];
@@ -53,15 +59,18 @@ __global__ void __launch_bounds__(BW_THREADS) idw_batch_kernel(
                 else
                     id = 0;
             }
-            s_w[tl * k_use + j] = w;
-            s_idx[tl * k_use + j] = id;
+            s_ent[tl * k_use + j].w = w;
+            s_ent[tl * k_use + j].off = (unsigned long long)(id * stride_i) * sizeof(V);
             wsum += w;
         }
         wsum = warp_sum(wsum);
-        for (int j = lane; j < k_use; j += 32) s_w[tl * k_use + j] /= wsum;
         __syncwarp();
         double wn = 0.0;
-        for (int j = lane; j < k_use; j += 32) wn += s_w[tl * k_use + j];
+        for (int j = lane; j < k_use; j += 32) {
+            const double w = s_ent[tl * k_use + j].w / wsum;
+            s_ent[tl * k_use + j].w = w;
+            wn += w;
+        }
         wn = warp_sum(wn);
         if (lane == 0) s_wsum[tl] = wn;
     }
@@ -71,29 +80,29 @@ __global__ void __launch_bounds__(BW_THREADS) idw_batch_kernel(
     for (long long t0 = 0; t0 < n_batch; t0 += 32) {
         const long long t = t0 + lane;
         const bool tin = t < n_batch;
+        const char* lane_base = reinterpret_cast<const char*>(vals) + (tin ? t : 0) * stride_t * (long long)sizeof(V);
         for (int tl = warp; tl < BW_TARGETS; tl += BW_WARPS) {
-            const double* w = s_w + tl * k_use;
-            const int* id = s_idx + tl * k_use;
+            const NbrEntry* e = s_ent + tl * k_use;
             V r;
             if (!check) {
                 double acc = 0.0;
-                if (tin) {
-#pragma unroll 4
-                    for (int j = 0; j < k_use; ++j)
-                        acc = fma(w[j], (double)vals[(long long)id[j] * stride_i + t * stride_t], acc);
+#pragma unroll 8
+                for (int j = 0; j < k_use; ++j) {
+                    const NbrEntry q = e[j];
+                    acc = fma(q.w, (double)*reinterpret_cast<const V*>(lane_base + q.off), acc);
                 }
                 r = (V)(acc / s_wsum[tl]);
             } else {
                 double num = 0.0, den = 0.0;
                 int fin = 0;
-                if (tin) {
-                    for (int j = 0; j < k_use; ++j) {
-                        const double v = (double)vals[(long long)id[j] * stride_i + t * stride_t];
-                        if (isfinite(v)) {
-                            num = fma(w[j], v, num);
-                            den += w[j];
-                            ++fin;
-                        }
+#pragma unroll 4
+                for (int j = 0; j < k_use; ++j) {
+                    const NbrEntry q = e[j];
+                    const double v = (double)*reinterpret_cast<const V*>(lane_base + q.off);
+                    if (isfinite(v) && q.w > 0.0) {
+                        num = fma(q.w, v, num);
+                        den += q.w;
+                        ++fin;
                     }
                 }
                 r = (fin < k_min || den == 0.0) ? quiet_nan<V>() : (V)(num / den);
@@ -187,8 +196,7 @@ int idw_from_table(const int* idx, const double* dd, int dist_is_squared, long l
         flag_nonfinite_kernel<V><<<fblocks, 256, 0, stream>>>(vals, n_samples * n_batch, flag_scratch);
         note_launch();
     }
-    const size_t smem = (size_t)BW_TARGETS * k_use * (sizeof(double) + sizeof(int)) + BW_TARGETS * sizeof(double) +
-                        32 * 33 * sizeof(V);
+    const size_t smem = (size_t)BW_TARGETS * k_use * sizeof(NbrEntry) + BW_TARGETS * sizeof(double) + 32 * 33 * sizeof(V);
     const long long blocks = (M + BW_TARGETS - 1) / BW_TARGETS;
     if (smem > 48 * 1024)
         CMX_CUDA(cudaFuncSetAttribute(idw_batch_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
