@@ -304,7 +304,9 @@ def main():
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop()
     launches = K.launch_count()
-    knn_ms, knn_n = K.kernel_time(K.KERNEL_KNN)
+    knn_ms, knn_n = _read_kernel(K, K.KERNEL_KNN)
+    k2_ms, k2_n = _read_kernel(K, K.KERNEL_IDW_BATCH)
+    k4_ms, k4_n = _read_kernel(K, K.KERNEL_OK_SOLVE)
     K.kernel_timing(False)
     if world > 1:
         tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -339,6 +341,26 @@ def main():
         "traffic": traffic,
     }
 
+    # secondary kernels of the step, for context: K2 against the measured HBM copy peak, K4 as a rate
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak, hbm_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    if os.path.exists(peaks_path):
+        try:
+            hbm_peak, hbm_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:  # noqa: BLE001
+            pass
+    other = {}
+    if k2_n:
+        bytes_k2 = rows_local * n_lon * (t * 8 + 12 * k)  # output written + [M][k] table read
+        gbs = bytes_k2 / (k2_ms / k2_n * 1e-3) / 1e9
+        other["idw_batch_kernel"] = {"bound": "hbm (nominally; on-chip gather bound at k=32, see DESIGN.md)", "achieved": gbs,
+                                     "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": hbm_src,
+                                     "kernel_ms_avg": k2_ms / k2_n, "share_of_step": (k2_ms / k2_n) / ms_per_step}
+    if k4_n:
+        other["ok_solve_kernel"] = {"kernel_ms_avg": k4_ms / k4_n, "targets_per_s": rows_local * n_lon / (k4_ms / k4_n * 1e-3),
+                                    "share_of_step": (k4_ms / k4_n) / ms_per_step}
+    roofline["other_kernels"] = other
+
     # ---------------- end to end through the public API with host buffers ----------------
     e2e = None
     if not args.no_e2e:
@@ -366,6 +388,10 @@ def main():
     if world > 1:
         os.dup2(2, 1)
         dist.destroy_process_group()
+
+
+def _read_kernel(K, kind):
+    return K.kernel_time(kind)
 
 
 def ok_step(K, torch, dev, inp, s_lat, s_lon, vals, t_lat_d, t_lon_d, r0, r1, k, world):

@@ -42,11 +42,10 @@ struct KnnJob {
     double* dist_out;  // [M][k]  sqrt(d2)
     double* d2_out;    // [M][k]  exact squared distance
     // fused IDW epilogue (idw.py:163-180); mode 0 = off
-    int idw_mode;      // 1: single slice -> out[M];  2: write normalised weights -> w_out[M][k]
+    int idw_mode;      // 1: single slice -> out[M] (weights + weighted mean in the kernel's epilogue)
     int value_is_f32;  // dtype of vals/out
     const void* vals;  // [N] (mode 1)
     void* out;         // [M] (mode 1)
-    double* w_out;     // [M][k] (mode 2)
     int k_min;
     double power;
     // scratch

@@ -47,7 +47,10 @@ constexpr int THREADS = WARPS * 32;
 #define CMX_UNROLL_PRAGMA CMX_STR(unroll CMX_UNROLL)
 constexpr int SS = CMX_SS;           // samples per (warp-private) shared-memory stage
 constexpr int GRP = 32;              // samples per filter group (= one per lane in the re-examination)
-constexpr int CAP = 64;              // candidate slots per target
+#ifndef CMX_CAP
+#define CMX_CAP 128
+#endif
+constexpr int CAP = CMX_CAP;         // candidate slots per target
 constexpr int FLUSH_AT = CAP - GRP;  // re-rank a target once it holds more than this
 constexpr int MAX_CTAS_PER_SM = CMX_CTAS;
 // resident CTAs per SM: the 16-targets-per-thread variant (large N) needs 128 registers
@@ -449,6 +452,7 @@ __global__ void __launch_bounds__(THREADS, ctas_per_sm(QPT)) knn_kernel(const __
     const int gwarp = blockIdx.x * WARPS + warp;
     const long long slot0 = (long long)gwarp * TQW;  // + q*32 + lane
     const SeedGrid seed = *a.seed;
+    unsigned* const cand_w = a.cand + slot0 * CAP;  // this warp's candidate buffers
 
     // warps fetch tiles from a global counter: early finishers take the remainder, which evens out the
     // load when the tile count is not a multiple of the resident warps (multi-GPU bands)
@@ -464,7 +468,7 @@ __global__ void __launch_bounds__(THREADS, ctas_per_sm(QPT)) knn_kernel(const __
         const int st_end = min(n_st, st_begin + st_per_seg);
         // ---------------- targets of this thread ----------------
         float Qa[QPT], Qb[COLSHARE ? 1 : QPT], thr[QPT];
-        unsigned offp[(QPT + 3) / 4];  // candidate counts, 8 bits per target (<= CAP = 64)
+        unsigned offp[(QPT + 3) / 4];  // candidate counts, 8 bits per target (<= CAP <= 128)
 #pragma unroll
         for (int i = 0; i < (QPT + 3) / 4; ++i) offp[i] = 0u;
         unsigned validm = 0, has_list = 0;
@@ -626,8 +630,8 @@ __global__ void __launch_bounds__(THREADS, ctas_per_sm(QPT)) knn_kernel(const __
                             const float t = fmaf(qa2, xa, fmaf(qb2, xb, xs));
                             const bool pass = t < th;
                             const unsigned pm = __ballot_sync(kFull, pass);
-                            const long long slot = slot0 + q * 32 + L;
-                            if (pass) a.cand[slot * CAP + o + __popc(pm & lt_mask)] = jbase + (unsigned)(g0 + lane);
+                            // 32-bit offset from the warp's candidate base: (q*32 + L)*CAP + o + rank among the passing lanes
+                            if (pass) cand_w[(unsigned)((q * 32 + L) * CAP + o) + __popc(pm & lt_mask)] = jbase + (unsigned)(g0 + lane);
                             int no = o + __popc(pm);
                             float nthr = th;
                             const bool full = no > FLUSH_AT;

@@ -129,11 +129,10 @@ def kernel_timing(enable: bool) -> None:
 
 
 def kernel_time(kind: int):
-    """(total milliseconds, launches) of one kernel kind since ``kernel_timing(True)`` / the last read."""
+    """(total milliseconds, launches) of one kernel kind since ``kernel_timing(True)``."""
     lib = _lib.load()
     ms, n = ctypes.c_double(0.0), ctypes.c_int64(0)
     _lib.check(lib.cmx_timing_read(kind, ctypes.byref(ms), ctypes.byref(n)), "cmx_timing_read")
-    lib.cmx_timing_reset()
     return ms.value, n.value
 
 
