@@ -214,26 +214,65 @@ __global__ void seed_colscan_kernel(const SeedGrid* g, int* sat) {
 // Rigorous upper bound on the squared distance from (ta, tb) to its k-th nearest sample:
 // grow a box of cells around the target's cell until it holds >= k samples; every one of
 // them is no farther than the farthest corner of that box.
+// samples in the clipped cell box [la, ha] x [lb, hb]
+__device__ __forceinline__ int seed_box_count(const SeedGrid& s, const int* __restrict__ sat, int la, int ha, int lb,
+                                              int hb) {
+    la = max(la, 0);
+    lb = max(lb, 0);
+    ha = min(ha, s.ga - 1);
+    hb = min(hb, s.gb - 1);
+    if (ha < la || hb < lb) return 0;
+    return sat[(size_t)(ha + 1) * SAT_LD + (hb + 1)] - sat[(size_t)la * SAT_LD + (hb + 1)] -
+           sat[(size_t)(ha + 1) * SAT_LD + lb] + sat[(size_t)la * SAT_LD + lb];
+}
+
+// farthest squared distance from (ta, tb) to any point of the cell box [la, ha] x [lb, hb] (clipped), inflated
+__device__ __forceinline__ double seed_box_far2(const SeedGrid& s, double ta, double tb, int la, int ha, int lb, int hb) {
+    la = max(la, 0);
+    lb = max(lb, 0);
+    ha = min(ha, s.ga - 1);
+    hb = min(hb, s.gb - 1);
+    const double A_lo = s.a0 + la * s.h, A_hi = s.a0 + (ha + 1) * s.h;
+    const double B_lo = s.b0 + lb * s.h, B_hi = s.b0 + (hb + 1) * s.h;
+    const double slack = 1e-9 * (s.h + fabs(A_lo) + fabs(A_hi) + fabs(B_lo) + fabs(B_hi));
+    const double da = fmax(fabs(ta - A_lo), fabs(A_hi - ta)) + slack;
+    const double db = fmax(fabs(tb - B_lo), fabs(B_hi - tb)) + slack;
+    return (da * da + db * db) * (1.0 + 1e-9);
+}
+
+// Rigorous upper bound on the squared distance from (ta, tb) to its k-th nearest sample: grow a region
+// of cells around the target's cell until the table says it holds >= k samples; every one of them is no
+// farther than the farthest point of that region.  Two region shapes are tried and the tighter bound
+// wins: a square box (area / enclosing-disc ratio 2/pi) and a plus-shaped union of two rectangles
+// (ratio ~0.79), which hugs the disc better and typically cuts the candidates per target by ~20 %.
 __device__ __forceinline__ double seed_bound_d2(const SeedGrid& s, const int* __restrict__ sat, double ta,
                                                 double tb, int k) {
     if (!s.valid) return CMX_INF;
     const int ia = seed_cell(ta, s.a0, s.inv_h, s.ga), ib = seed_cell(tb, s.b0, s.inv_h, s.gb);
     const int wmax = max(s.ga, s.gb);
-    for (int w = 0;; w = w < 8 ? w + 1 : w * 2) {
-        const int la = max(ia - w, 0), ha = min(ia + w, s.ga - 1);
-        const int lb = max(ib - w, 0), hb = min(ib + w, s.gb - 1);
-        const int cnt = sat[(size_t)(ha + 1) * SAT_LD + (hb + 1)] - sat[(size_t)la * SAT_LD + (hb + 1)] -
-                        sat[(size_t)(ha + 1) * SAT_LD + lb] + sat[(size_t)la * SAT_LD + lb];
-        if (cnt >= k) {
-            const double A_lo = s.a0 + la * s.h, A_hi = s.a0 + (ha + 1) * s.h;
-            const double B_lo = s.b0 + lb * s.h, B_hi = s.b0 + (hb + 1) * s.h;
-            const double slack = 1e-9 * (s.h + fabs(A_lo) + fabs(A_hi) + fabs(B_lo) + fabs(B_hi));
-            const double da = fmax(fabs(ta - A_lo), fabs(A_hi - ta)) + slack;
-            const double db = fmax(fabs(tb - B_lo), fabs(B_hi - tb)) + slack;
-            return (da * da + db * db) * (1.0 + 1e-9);
-        }
+    int w = 0;
+    for (;; w = w < 8 ? w + 1 : w * 2) {
+        if (seed_box_count(s, sat, ia - w, ia + w, ib - w, ib + w) >= k) break;
         if (w >= wmax) return CMX_INF;  // fewer than k finite samples in total
     }
+    double best = seed_box_far2(s, ta, tb, ia - w, ia + w, ib - w, ib + w);
+    if (w >= 2 && w <= 64) {
+        // plus shape: [ia-A, ia+A] x [ib-B, ib+B]  U  [ia-B, ia+B] x [ib-A, ib+A],  B ~ 0.6 A
+        for (int A = w; A <= w + (w >> 1) + 1; ++A) {
+            const int B = (3 * A + 2) / 5;
+            const int cnt = seed_box_count(s, sat, ia - A, ia + A, ib - B, ib + B) +
+                            seed_box_count(s, sat, ia - B, ia + B, ib - A, ib + A) -
+                            seed_box_count(s, sat, ia - B, ia + B, ib - B, ib + B);
+            if (cnt >= k) {
+                // both rectangles are contained in the disc around the target through their far corners
+                const double f1 = seed_box_far2(s, ta, tb, ia - A, ia + A, ib - B, ib + B);
+                const double f2 = seed_box_far2(s, ta, tb, ia - B, ia + B, ib - A, ib + A);
+                best = fmin(best, fmax(f1, f2));
+                break;
+            }
+        }
+    }
+    return best;
 }
 
 // ------------------------------------------------------------------------------------------
