@@ -200,6 +200,9 @@ def main():
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--search", default="brute", choices=["brute", "binned"],
+                    help="neighbour search of the headline numbers: K1 brute force (north_star) or K1c cell-binned")
+    ap.add_argument("--no-binned", action="store_true", help="skip the extra K1c (binned search) measurement")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -287,32 +290,38 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 0)):
-        step()
-    barrier()
-    K.reset_launch_count()
-    K.kernel_timing(True)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        out = step()
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop()
-    launches = K.launch_count()
-    knn_ms, knn_n = _read_kernel(K, K.KERNEL_KNN)
-    k2_ms, k2_n = _read_kernel(K, K.KERNEL_IDW_BATCH)
-    k4_ms, k4_n = _read_kernel(K, K.KERNEL_OK_SOLVE)
-    K.kernel_timing(False)
-    if world > 1:
-        tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms_total = float(tmax.item())
-    ms_per_step = ms_total / args.steps
+    def measure(search, steps, warmup):
+        K.set_search(search)
+        for _ in range(max(warmup, 0)):
+            step()
+        barrier()
+        K.reset_launch_count()
+        K.kernel_timing(True)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        r = {"clocks": sampler.stop(), "launches": K.launch_count(),
+             "knn": _read_kernel(K, K.KERNEL_KNN), "knn_binned": _read_kernel(K, K.KERNEL_KNN_BINNED),
+             "k2": _read_kernel(K, K.KERNEL_IDW_BATCH), "k4": _read_kernel(K, K.KERNEL_OK_SOLVE)}
+        K.kernel_timing(False)
+        if world > 1:
+            tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            ms_total = float(tmax.item())
+        r["ms_per_step"] = ms_total / steps
+        return r
+
+    main_run = measure(args.search, args.steps, args.warmup)
+    clocks, launches, ms_per_step = main_run["clocks"], main_run["launches"], main_run["ms_per_step"]
+    (knn_ms, knn_n), (k2_ms, k2_n), (k4_ms, k4_n) = main_run["knn"], main_run["k2"], main_run["k4"]
+    knb_ms, knb_n = main_run["knn_binned"]
     value = m / (ms_per_step * 1e-3)
 
     # ---------------- roofline of the dominant kernel (K1 neighbour search, FP32 pipe) ----------------
@@ -359,12 +368,50 @@ def main():
     if k4_n:
         other["ok_solve_kernel"] = {"kernel_ms_avg": k4_ms / k4_n, "targets_per_s": rows_local * n_lon / (k4_ms / k4_n * 1e-3),
                                     "share_of_step": (k4_ms / k4_n) / ms_per_step}
+    fused = (t == 1 and method == "idw")
+    knb_bytes = 36.0 * n + rows_local * n_lon * (8.0 if fused else 12.0 * k)  # counting sort r/w + output
+
+    def binned_entry(ms_avg, step_ms):
+        gbs = knb_bytes / (ms_avg * 1e-3) / 1e9
+        return {"bound": "hbm (nominally; pruned search is instruction-issue bound, see DESIGN.md K1c)", "achieved": gbs,
+                "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": hbm_src,
+                "kernel_ms_avg": ms_avg, "share_of_step": ms_avg / step_ms,
+                "targets_per_s": rows_local * n_lon / (ms_avg * 1e-3)}
+
+    if knb_n:
+        if not knn_n:  # headline measured with --search binned: K1c (or K2) is the dominant kernel
+            ent = binned_entry(knb_ms / knb_n, ms_per_step)
+            roofline = {"kernel": "knn_binned_kernel (K1c: cell-binned neighbour search, counting sort included)",
+                        "bound": "hbm", "achieved": ent["achieved"], "peak": hbm_peak, "unit": "GB/s", "frac": ent["frac"],
+                        "peak_source": hbm_src, "algorithmic_bytes_per_launch": knb_bytes, "kernel_ms_avg": ent["kernel_ms_avg"],
+                        "launches_timed": knb_n, "share_of_step": ent["share_of_step"], "traffic": None,
+                        "note": ent["bound"]}
+        else:
+            other["knn_binned_kernel"] = binned_entry(knb_ms / knb_n, ms_per_step)
     roofline["other_kernels"] = other
 
     # ---------------- end to end through the public API with host buffers ----------------
     e2e = None
     if not args.no_e2e:
         e2e = e2e_run(args, inp, rank, world, r0, r1, dev, method)
+
+    # ---------------- the same workload with the cell-binned search (K1c) ----------------
+    binned = None
+    if args.search == "brute" and not args.no_binned:
+        b = measure("binned", args.steps, args.warmup)
+        binned = {"value": m / (b["ms_per_step"] * 1e-3), "unit": "targets/s", "ms_per_step": b["ms_per_step"],
+                  "gpu_launches": int(b["launches"]),
+                  "what": "identical step with cmx_set_search(CMX_SEARCH_BINNED): same neighbour tables and fields, "
+                          "samples counting-sorted into grid cells, each target scans only the cells its k-th-distance bound touches"}
+        if b["knn_binned"][1]:
+            binned["knn_binned_kernel"] = binned_entry(b["knn_binned"][0] / b["knn_binned"][1], b["ms_per_step"])
+        if b["k2"][1]:
+            binned["idw_batch_kernel_ms_avg"] = b["k2"][0] / b["k2"][1]
+        if b["k4"][1]:
+            binned["ok_solve_kernel_ms_avg"] = b["k4"][0] / b["k4"][1]
+        if not args.no_e2e:
+            binned["e2e"] = e2e_run(args, inp, rank, world, r0, r1, dev, method)
+        K.set_search(args.search)
 
     # ---------------- CPU baseline on the box's host cores (rank 0, N = 1 only) ----------------
     cpu = None
@@ -381,7 +428,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "output_values_per_s": value * t, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "search": args.search, "binned_search": binned,
             "notes": "fp32 distance filter + exact float64 re-rank; values/output float64; NCCL all-gather of output slabs inside the step for N>1",
         }
         print(json.dumps(line), flush=True)

@@ -31,6 +31,20 @@ from .idw import IDWReconstructor  # noqa: F401
 from .kriging import OrdinaryKrigingReconstructor  # noqa: F401
 
 
+def set_search(algorithm: str) -> str:
+    """Neighbour search used by both reconstructors: ``"brute"`` (K1, default) or ``"binned"`` (K1c, cell-binned;
+    same results, ~N/k times fewer distance evaluations).  Returns the previous setting."""
+    from . import kernels
+
+    return kernels.set_search(algorithm)
+
+
+def get_search() -> str:
+    from . import kernels
+
+    return kernels.get_search()
+
+
 def install_into_climatrix() -> bool:
     """Register the GPU reconstructors in a real climatrix installation.
 

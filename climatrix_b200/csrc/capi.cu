@@ -8,9 +8,11 @@ namespace cmx {
 namespace {
 thread_local long long g_launches = 0;
 thread_local char g_cuda_err[256] = "";
+thread_local int g_search = CMX_SEARCH_BRUTE;
 }  // namespace
 
 void note_launch() { ++g_launches; }
+int search_algorithm() { return g_search; }
 
 int cuda_fail(cudaError_t e) {
     snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
@@ -24,15 +26,15 @@ int check_launch() {
 
 // ---- optional per-kernel timing -------------------------------------------------------
 namespace {
-constexpr int kKinds = 3;
+constexpr int kKinds = 4;
 constexpr int kMaxPairs = 256;
 struct TimingState {
     bool on = false;
     cudaEvent_t ev[kKinds][kMaxPairs][2];
-    int made[kKinds] = {0, 0, 0};
-    int used[kKinds] = {0, 0, 0};
-    long long dropped[kKinds] = {0, 0, 0};
-    bool open[kKinds] = {false, false, false};
+    int made[kKinds] = {};
+    int used[kKinds] = {};
+    long long dropped[kKinds] = {};
+    bool open[kKinds] = {};
 } g_timing;
 }  // namespace
 
@@ -102,6 +104,14 @@ const char* cmx_strerror(int code) {
 }
 
 const char* cmx_last_cuda_error(void) { return cmx::g_cuda_err; }
+
+int cmx_set_search(int algorithm) {
+    if (algorithm != CMX_SEARCH_BRUTE && algorithm != CMX_SEARCH_BINNED) return CMX_ERR_BAD_ARG;
+    const int prev = cmx::g_search;
+    cmx::g_search = algorithm;
+    return prev;
+}
+int cmx_get_search(void) { return cmx::g_search; }
 
 int64_t cmx_launch_count(void) { return cmx::g_launches; }
 void cmx_reset_launch_count(void) { cmx::g_launches = 0; }

@@ -13,6 +13,7 @@ constexpr unsigned kFull = 0xffffffffu;
 
 // ---- host-side bookkeeping (thread-local) ---------------------------------
 void note_launch();                 // ++launch counter
+int search_algorithm();             // CMX_SEARCH_* selected by cmx_set_search on this thread
 int cuda_fail(cudaError_t e);       // records text, returns CMX_ERR_CUDA
 int check_launch();                 // cudaGetLastError() -> CMX_OK / CMX_ERR_CUDA
 int sm_count();                     // SMs of the current device (cached)

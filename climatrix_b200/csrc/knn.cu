@@ -97,6 +97,11 @@ struct KnnArgs {
     int nseg;
     double* part_d;
     int* part_i;
+    // cell-binned search (K1c): samples counting-sorted by seed-grid cell (row-major cell order)
+    int* bin_cursor;     // [ga * gb] fill cursors of the scatter
+    double* bin_a;       // [N] sorted copies of the sample coordinates
+    double* bin_b;
+    int* bin_idx;        // [N] original sample index of each sorted slot
 };
 
 // ------------------------------------------------------------------------------------------
@@ -762,6 +767,157 @@ __global__ void __launch_bounds__(256) knn_merge_kernel(const __grid_constant__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K1c: cell-binned search.  The summed-area table already holds, for every cell, how many samples lie
+// in the rows before it and in its own row to the left of it, so the start of cell (r, c) in a
+// row-major counting sort is  S[r][gb] + S[r+1][c] - S[r][c]  - no separate prefix scan is needed.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int bin_cell_start(const int* __restrict__ sat, int gb, int r, int c) {
+    const int* S0 = sat + (size_t)r * SAT_LD;
+    return S0[gb] + S0[SAT_LD + c] - S0[c];
+}
+
+__global__ void bin_scatter_kernel(const double* __restrict__ sa, const double* __restrict__ sb, long long n,
+                                   const SeedGrid* g, const int* __restrict__ sat, int* cursor,
+                                   double* __restrict__ bin_a, double* __restrict__ bin_b, int* __restrict__ bin_idx) {
+    const SeedGrid s = *g;
+    if (!s.valid) return;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double a = sa[i], b = sb[i];
+        if (isfinite(a) && isfinite(b)) {
+            const int ia = seed_cell(a, s.a0, s.inv_h, s.ga), ib = seed_cell(b, s.b0, s.inv_h, s.gb);
+            const int pos = bin_cell_start(sat, s.gb, ia, ib) + atomicAdd(&cursor[(size_t)ia * s.gb + ib], 1);
+            bin_a[pos] = a;
+            bin_b[pos] = b;
+            bin_idx[pos] = (int)i;
+        }
+    }
+}
+
+// One warp per target.  The seed bound D2 >= (k-th nearest distance)^2 is rigorous, so every one of the k
+// nearest samples lies in the cells that the square [t - D, t + D]^2 touches; in the sorted order each cell
+// row of that square is one contiguous segment.  Lanes own one cell row each to look the segments up, the
+// segments are then flattened so that all 32 lanes evaluate exact float64 distances, and candidates within the
+// running k-th distance go through the same bitonic sort / merge network as K1's re-rank.  The order of the
+// samples inside a cell (atomics in the scatter) cannot change the result: the list is the lexicographic
+// (d2, index) top-k of a candidate set that always contains the true top-k.
+template <int E>
+__global__ void __launch_bounds__(256) knn_binned_kernel(const __grid_constant__ KnnArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const SeedGrid s = *a.seed;
+    const int* __restrict__ sat = a.sat;
+    const int k = a.j.k;
+    for (long long m = warp0; m < a.M; m += nwarps) {
+        double ta, tb;
+        if (a.j.grid) {
+            const long long row = m / a.j.n_b;
+            ta = a.j.t_a[row];
+            tb = a.j.t_b[m - row * a.j.n_b];
+        } else {
+            ta = a.j.t_a[m];
+            tb = a.j.t_b[m];
+        }
+        double ld[E];
+        int li[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            ld[e] = CMX_INF;
+            li[e] = INT_MAX;
+        }
+        int ra0 = 0, ra1 = -1, cb0 = 0, cb1 = -1;
+        double kth = CMX_INF;
+        if (s.valid) {
+            kth = seed_bound_d2(s, sat, ta, tb, k);
+            if (kth < CMX_INF) {
+                const double D = sqrt(kth) * (1.0 + 1e-12);
+                ra0 = seed_cell(ta - D, s.a0, s.inv_h, s.ga);
+                ra1 = seed_cell(ta + D, s.a0, s.inv_h, s.ga);
+                cb0 = seed_cell(tb - D, s.b0, s.inv_h, s.gb);
+                cb1 = seed_cell(tb + D, s.b0, s.inv_h, s.gb);
+            } else {  // fewer than k finite samples (or a non-finite target): look at everything
+                ra1 = s.ga - 1;
+                cb1 = s.gb - 1;
+            }
+        }
+        const int R = ra1 - ra0 + 1;
+        for (int rb = 0; rb < R; rb += 32) {
+            int lo = 0, len = 0;
+            if (rb + lane < R) {
+                const int* S0 = sat + (size_t)(ra0 + rb + lane) * SAT_LD;
+                const int left = S0[SAT_LD + cb0] - S0[cb0];
+                lo = S0[s.gb] + left;
+                len = (S0[SAT_LD + cb1 + 1] - S0[cb1 + 1]) - left;
+            }
+            int pre = len;  // inclusive prefix sum of the segment lengths
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(kFull, pre, o);
+                if (lane >= o) pre += u;
+            }
+            const int total = __shfl_sync(kFull, pre, 31);
+            const int excl = pre - len;
+            for (int j0 = 0; j0 < total; j0 += 32) {
+                const int j = j0 + lane;
+                int pos = 0;  // number of segments that end at or before j = the segment holding j
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const int v = __shfl_sync(kFull, pre, pos + step - 1);
+                    if (v <= j) pos += step;
+                }
+                const int p = __shfl_sync(kFull, lo, pos) + (j - __shfl_sync(kFull, excl, pos));
+                double d2 = CMX_INF;
+                if (j < total) {
+                    // bit-identical to cKDTree: plain float64 dx*dx + dy*dy, no FMA contraction
+                    const double da = __dsub_rn(ta, a.bin_a[p]);
+                    const double db = __dsub_rn(tb, a.bin_b[p]);
+                    d2 = __dadd_rn(__dmul_rn(da, da), __dmul_rn(db, db));
+                    if (!(d2 == d2)) d2 = CMX_INF;  // NaN never ranks
+                }
+                // ties at the k-th distance are resolved by index inside the merge, so '<=' here
+                const bool c = d2 <= kth && d2 < CMX_INF;
+                if (__any_sync(kFull, c)) {
+                    double cd = c ? d2 : CMX_INF;
+                    int ci = c ? a.bin_idx[p] : INT_MAX;
+                    warp_sort32(cd, ci, lane);
+                    merge_sorted32<E>(ld, li, cd, ci, lane);
+                    double sel = ld[0];
+#pragma unroll
+                    for (int e = 1; e < E; ++e)
+                        if (((k - 1) >> 5) == e) sel = ld[e];
+                    kth = fmin(kth, __shfl_sync(kFull, sel, (k - 1) & 31));
+                }
+            }
+        }
+        const double r = finish_target<E>(a, lane, m, ld, li);
+        if (a.j.idw_mode == 1 && lane == 0) {
+            if (a.j.value_is_f32)
+                static_cast<float*>(a.j.out)[m] = (float)r;
+            else
+                static_cast<double*>(a.j.out)[m] = r;
+        }
+    }
+}
+
+template <int E>
+int launch_binned(const KnnArgs& args, cudaStream_t stream) {
+    const int sms = sm_count();
+    const long long pre = (args.j.n + 255) / 256;
+    const int pre_blocks = (int)(pre < (long long)sms * 8 ? pre : (long long)sms * 8);
+    timing_begin(CMX_KERNEL_KNN_BINNED, stream);
+    CMX_CUDA(cudaMemsetAsync(args.bin_cursor, 0, (size_t)GMAX * GMAX * sizeof(int), stream));
+    bin_scatter_kernel<<<pre_blocks, 256, 0, stream>>>(args.j.s_a, args.j.s_b, args.j.n, args.seed, args.sat,
+                                                       args.bin_cursor, args.bin_a, args.bin_b, args.bin_idx);
+    const long long blocks = (args.M * 32 + 255) / 256;
+    const long long cap = (long long)sms * 8;
+    knn_binned_kernel<E><<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, stream>>>(args);
+    timing_end(CMX_KERNEL_KNN_BINNED, stream);
+    note_launch();
+    note_launch();
+    return check_launch();
+}
+
 template <int E, int QPT>
 int launch(const KnnArgs& args, int ctas, cudaStream_t stream) {
     const size_t smem = WARPS * WARP_SMEM;
@@ -914,6 +1070,25 @@ int run_knn(const KnnJob& job, cudaStream_t stream) {
     if (rc != CMX_OK) return rc;
 
     const int e = list_slots(job.k);
+    if (search_algorithm() == CMX_SEARCH_BINNED) {
+        // K1c borrows K1's (unused) list / candidate scratch: cursors, sorted coordinates, original indices
+        unsigned char* b = ws;
+        args.bin_cursor = reinterpret_cast<int*>(b);
+        b += (size_t)GMAX * GMAX * sizeof(int);
+        args.bin_a = reinterpret_cast<double*>(b);
+        b += (size_t)job.n * sizeof(double);
+        args.bin_b = reinterpret_cast<double*>(b);
+        b += (size_t)job.n * sizeof(double);
+        args.bin_idx = reinterpret_cast<int*>(b);
+        b += (size_t)job.n * sizeof(int);
+        if (b <= ws_end) {
+            args.nseg = 1;
+            if (e == 1) return launch_binned<1>(args, stream);
+            if (e == 2) return launch_binned<2>(args, stream);
+            return launch_binned<4>(args, stream);
+        }
+        // does not fit (N beyond ~5e7 with the base workspace): K1 returns the same table
+    }
 #define CMX_DISPATCH(Q)                                            \
     do {                                                           \
         if (e == 1) return launch<1, Q>(args, ctas, stream);       \

@@ -400,6 +400,351 @@ __global__ void __launch_bounds__(512) ok_solve_team_kernel(const OkArgs a, int 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K4 for k <= 64: the window's matrix lives in REGISTERS, one row per thread.
+//
+// The shared-memory kernels above move every matrix element through shared memory twice per
+// elimination step (k^3 loads + k^3 stores per window); at k = 64 that traffic, not the FP64 pipe,
+// sets the pace.  Here thread r keeps row r of [b | 1 | G] in registers: a[0], a[1] are the two
+// right-hand sides, a[2..] the not yet eliminated columns.  Each step the rows shift left by one
+// (the update writes a[j-1] = a[j] - f * pivot[j]), so the active column is always a[2] and every
+// register index is a compile-time constant although the step loop is a run-time loop; the code is
+// specialised per phase of 8 steps (row length shrinks by 8 per phase), which keeps the wasted
+// multiply-adds on dead tail columns to ~10 %.  Only the pivot row goes through shared memory: the
+// best row of each warp publishes itself, one named barrier per step, all threads read it back by
+// broadcast.  Same pivot rule (largest magnitude, lowest row on ties), same true division, same fma
+// as the shared-memory kernels: results are bit-identical to them.
+// FP64-pipe bound: ~ sum_c (k - c + 2) ~ k^2/2 fma per thread per window.
+// ------------------------------------------------------------------------------------------
+struct VarioConst {
+    int model;
+    double p0, p1, p2, c0, c1;
+};
+__device__ __forceinline__ VarioConst vario_const(int model, double p0, double p1, double p2) {
+    VarioConst v{model, p0, p1, p2, 0.0, 0.0};
+    if (model == CMX_VARIOGRAM_GAUSSIAN) {
+        const double r = p1 * 4.0 / 7.0;
+        v.c0 = 1.0 / (r * r);
+    } else if (model == CMX_VARIOGRAM_SPHERICAL) {
+        v.c0 = 3.0 / (2.0 * p1);
+        v.c1 = 1.0 / (2.0 * p1 * p1 * p1);
+    } else if (model == CMX_VARIOGRAM_EXPONENTIAL) {
+        v.c0 = 1.0 / (p1 / 3.0);
+    }
+    return v;
+}
+// gamma_of with the divisions by constants hoisted (differs from it by rounding only)
+__device__ __forceinline__ double gamma_pre(const VarioConst& v, double d) {
+    switch (v.model) {
+        case CMX_VARIOGRAM_LINEAR:
+            return v.p0 * d + v.p1;
+        case CMX_VARIOGRAM_POWER:
+            return v.p0 * pow(d, v.p1) + v.p2;
+        case CMX_VARIOGRAM_GAUSSIAN:
+            return v.p0 * (1.0 - exp(-(d * d) * v.c0)) + v.p2;
+        case CMX_VARIOGRAM_SPHERICAL:
+            if (d <= v.p1) return v.p0 * (d * v.c0 - (d * d * d) * v.c1) + v.p2;
+            return v.p0 + v.p2;
+        default:
+            return v.p0 * (1.0 - exp(-d * v.c0)) + v.p2;
+    }
+}
+
+#ifndef CMX_ROWS_SPEC_RCP
+#define CMX_ROWS_SPEC_RCP 1
+#endif
+struct RowState {
+    bool done, singular;
+    double diag;
+    int mycol;
+};
+
+// Pivot search for one step + publication of this warp's candidate row (its reciprocal pivot in the spare slot).
+// Magnitudes of non-negative doubles order like their bit patterns, so the arg-max is two REDUX and a ballot.
+template <int KC, int L>
+__device__ __forceinline__ void rows_publish(const double (&a)[KC + 2], const RowState& st, int c, int k, int r, int lane,
+                                             int wsub, double cand, double rinv, double* prow,
+                                             unsigned long long* pbest, int* pbrow) {
+    constexpr int NW = (KC + 31) / 32;
+    constexpr int LS = KC + 4;  // stride of a published row: KC + 2 values, 1 / pivot, pad
+    const unsigned long long bits = (st.done || r >= k) ? 0ull : (unsigned long long)__double_as_longlong(fabs(cand));
+    const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+    const unsigned mh = __reduce_max_sync(kFull, hi);
+    const unsigned ml = __reduce_max_sync(kFull, hi == mh ? lo : 0u);
+    const unsigned win = __ballot_sync(kFull, hi == mh && lo == ml);
+    const int wl = __ffs(win) - 1;  // lowest row of the warp among equal maxima
+    const int buf = c & 1;
+    double* slot = prow + (size_t)(buf * NW + wsub) * LS;
+    if (lane == wl) {
+#pragma unroll
+        for (int j = 0; j < L; j += 2) *reinterpret_cast<double2*>(slot + j) = make_double2(a[j], a[j + 1]);
+        slot[KC + 2] = rinv;
+        pbest[buf * NW + wsub] = ((unsigned long long)mh << 32) | ml;
+        pbrow[buf * NW + wsub] = wsub * 32 + wl;
+    }
+}
+
+// 8 elimination steps (fewer at the end of the window) on rows of current length L = 2 + remaining columns.
+// On entry the candidates of step c0 are already published.  Inside a step the first multiply-add produces the
+// next active column; the next pivot search and every thread's speculative reciprocal of its own candidate are
+// issued right behind it, so their latency hides under the remaining multiply-adds of the step.
+template <int KC, int L>
+__device__ __forceinline__ void rows_phase(double (&a)[KC + 2], RowState& st, int c0, int k, int r, int lane, int wsub,
+                                           double* prow, unsigned long long* pbest, int* pbrow, int bar_id) {
+    constexpr int NW = (KC + 31) / 32;
+    constexpr int LS = KC + 4;
+#pragma unroll 1
+    for (int c = c0; c < c0 + 8 && c < k; ++c) {
+        if (NW > 1)
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * NW) : "memory");
+        else
+            __syncwarp();
+        const int buf = c & 1;
+        unsigned long long best = pbest[buf * NW];
+        int brow = pbrow[buf * NW];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) {
+            const unsigned long long ob = pbest[buf * NW + w];
+            if (ob > best) {  // equal maxima: the lower row (earlier warp) stays
+                best = ob;
+                brow = pbrow[buf * NW + w];
+            }
+        }
+        if (best == 0ull || best > 0x7ff0000000000000ull) {  // zero column (or NaN): singular window
+            st.singular = true;
+            return;
+        }
+        const double* prd = prow + (size_t)(buf * NW + (brow >> 5)) * LS;
+        const double2* pr = reinterpret_cast<const double2*>(prd);
+        const double2 p23 = pr[1];
+        const double pval = p23.x, pinv = prd[KC + 2];
+        const bool me = r == brow;
+        if (me) {
+            st.done = true;
+            st.diag = a[2];
+            st.mycol = c;
+        }
+        // f = a[2] / pval, correctly rounded from the published reciprocal (one Newton step on the quotient).
+        // Identical rows (duplicate samples, zero nugget) must cancel to exact zeros so that a singular window is
+        // detected, as LAPACK's exact-zero pivot test does for the reference: a[2] == pval gives exactly 1 here.
+        double f;
+#if CMX_ROWS_SPEC_RCP
+        if (best > 0x0360000000000000ull && best < 0x7c90000000000000ull) {  // ~1e-290 < |pval| < ~1e290
+            const double q = a[2] * pinv;
+            f = fma(fma(-q, pval, a[2]), pinv, q);
+        } else {
+            f = a[2] / pval;
+        }
+#else
+        f = a[2] / pval;
+        (void)pinv;
+#endif
+        if (me) f = 0.0;
+        const double next = fma(-f, p23.y, a[3]);  // my entry of the next active column
+        const bool more = c + 1 < k;
+        double rinv = 0.0;
+#if CMX_ROWS_SPEC_RCP
+        if (more) rinv = __drcp_rn(next);
+#endif
+        const double2 p01 = pr[0];
+        a[0] = fma(-f, p01.x, a[0]);
+        a[1] = fma(-f, p01.y, a[1]);
+        a[2] = next;
+#pragma unroll
+        for (int j = 4; j < L; j += 2) {  // 16-byte broadcast loads of the published row
+            const double2 q = pr[j >> 1];
+            a[j - 1] = fma(-f, q.x, a[j]);
+            a[j] = fma(-f, q.y, a[j + 1]);
+        }
+        a[L - 1] = 0.0;
+        if (more) rows_publish<KC, L>(a, st, c + 1, k, r, lane, wsub, next, rinv, prow, pbest, pbrow);
+    }
+}
+
+template <int KC, int PH>
+__device__ __forceinline__ void rows_phases(double (&a)[KC + 2], RowState& st, int k, int r, int lane, int wsub,
+                                            double* prow, unsigned long long* pbest, int* pbrow, int bar_id) {
+    if constexpr (PH == 0) rows_publish<KC, KC + 2>(a, st, 0, k, r, lane, wsub, a[2], __drcp_rn(a[2]), prow, pbest, pbrow);
+    if constexpr (PH * 8 < KC) {
+        if (PH * 8 < k && !st.singular) {
+            rows_phase<KC, KC + 2 - 8 * PH>(a, st, PH * 8, k, r, lane, wsub, prow, pbest, pbrow, bar_id);
+            rows_phases<KC, PH + 1>(a, st, k, r, lane, wsub, prow, pbest, pbrow, bar_id);
+        }
+    }
+}
+
+template <int KC>
+__host__ __device__ constexpr size_t rows_team_smem() {
+    constexpr int NW = (KC + 31) / 32;
+    return (size_t)KC * NW * 32 * sizeof(double) + (size_t)4 * KC * sizeof(double) + (size_t)2 * NW * (KC + 4) * sizeof(double) + 2 * NW * sizeof(unsigned long long) +
+           4 * NW * sizeof(double) + 2 * NW * sizeof(int) + 8;
+}
+
+template <int KC, int TEAMS>
+__global__ void __launch_bounds__(TEAMS * ((KC + 31) / 32) * 32, KC > 32 ? 3 : 4) ok_solve_rows_kernel(const OkArgs a_) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NW = (KC + 31) / 32;
+    const OkArgs& A = a_;
+    const int k = A.k;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int team = warp / NW, wsub = warp % NW;
+    const int r = wsub * 32 + lane;
+    unsigned char* base = smem_raw + (size_t)team * ((rows_team_smem<KC>() + 15) & ~size_t(15));
+    constexpr int TH = NW * 32;
+    double* gmat = reinterpret_cast<double*>(base);  // [KC][TH]
+    double* cx = gmat + (size_t)KC * TH;
+    double* cy = cx + KC;
+    double* cz = cy + KC;
+    double* cb = cz + KC;
+    double* prow = cb + KC;                                             // [2][NW][KC + 4]
+    unsigned long long* pbest = reinterpret_cast<unsigned long long*>(prow + 2 * NW * (KC + 4));  // [2][NW]
+    double* red = reinterpret_cast<double*>(pbest + 2 * NW);           // [4][NW]
+    int* pbrow = reinterpret_cast<int*>(red + 4 * NW);                  // [2][NW]
+    const int bar_id = 1 + team;
+    auto team_barrier = [&]() {
+        if (NW > 1)
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * NW) : "memory");
+        else
+            __syncwarp();
+    };
+    const VarioConst vc = vario_const(A.model, A.p0, A.p1, A.p2);
+
+    const long long total_teams = (long long)gridDim.x * TEAMS;
+    for (long long m = (long long)blockIdx.x * TEAMS + team; m < A.M; m += total_teams) {
+        double mx = 0.0, my = 0.0, mz = 0.0, borig = 0.0;
+        if (r < k) {
+            int id = A.idx[m * k + r];
+            if (id < 0 || id >= A.n) {  // short neighbour list: duplicate row 0 -> singular window -> NaN
+                id = A.idx[m * k];
+                if (id < 0 || id >= A.n) id = 0;
+            }
+            mx = A.s_x[id];
+            my = A.s_y[id];
+            mz = A.z_is_f32 ? (double)static_cast<const float*>(A.z)[id] : static_cast<const double*>(A.z)[id];
+            const double bd = window_distance(A.metric, A.d2[m * k + r]);
+            double b = -gamma_pre(vc, bd);
+            if (A.exact_values && fabs(bd) <= OK_EPS) b = 0.0;
+            borig = b;
+        }
+        if (r < KC) {
+            cx[r] = mx;
+            cy[r] = my;
+            cz[r] = mz;
+            cb[r] = borig;
+        }
+        team_barrier();
+        // ---- G through shared memory once, [column][row]: G is symmetric, so thread r evaluates only the
+        // pairs (r, r+1..r+k/2 mod k) and stores each value at both places (strides of TH+1: conflict-free) ----
+        if (r < k) {
+            gmat[(size_t)r * TH + r] = 0.0;
+            const int half = k >> 1;
+            int j = r;
+            for (int t = 1; t <= half; ++t) {
+                j = j + 1 == k ? 0 : j + 1;
+                const double g = -gamma_pre(vc, sample_distance(A.metric, mx, my, cx[j], cy[j]));
+                gmat[(size_t)j * TH + r] = g;
+                gmat[(size_t)r * TH + j] = g;
+            }
+        }
+        team_barrier();
+        // ---- my row of [b | 1 | G] into registers ----
+        double a[KC + 2];
+        a[0] = borig;
+        a[1] = r < k ? 1.0 : 0.0;
+#pragma unroll
+        for (int j = 0; j < KC; ++j) a[2 + j] = (r < k && j < k) ? gmat[(size_t)j * TH + r] : 0.0;
+        RowState st{false, false, 1.0, 0};
+        if (k > 1) rows_phases<KC, 0>(a, st, k, r, lane, wsub, prow, pbest, pbrow, bar_id);
+
+        // ---- back out x, mu; estimate and variance (thread r holds the row that was pivot of column mycol) ----
+        double res = quiet_nan<double>(), var = quiet_nan<double>();
+        bool singular = st.singular;
+        if (k == 1) {
+            // the core is the 1x1 zero matrix while the bordered system [[0,1],[1,0]] is regular: x = 1, mu = b
+            res = cz[0] * A.out_scale + A.out_shift;
+            var = -(cb[0] + cb[0]);
+        } else if (!singular) {
+            double y = 0.0, u = 0.0;
+            if (r < k) {
+                const double dinv = 1.0 / st.diag;
+                y = a[0] * dinv;
+                u = a[1] * dinv;
+            }
+            double sy = warp_sum(y), su = warp_sum(u);
+            if (NW > 1) {
+                if (lane == 0) {
+                    red[0 * NW + wsub] = sy;
+                    red[1 * NW + wsub] = su;
+                }
+                team_barrier();
+                sy = su = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    sy += red[0 * NW + w];
+                    su += red[1 * NW + w];
+                }
+            }
+            const double mu = (sy - 1.0) / su;
+            const double x = y - mu * u;
+            double zz = 0.0, xb = 0.0;
+            if (r < k) {
+                zz = x * cz[st.mycol];
+                xb = x * cb[st.mycol];
+            }
+            zz = warp_sum(zz);
+            xb = warp_sum(xb);
+            if (NW > 1) {
+                if (lane == 0) {
+                    red[2 * NW + wsub] = zz;
+                    red[3 * NW + wsub] = xb;
+                }
+                team_barrier();
+                zz = xb = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    zz += red[2 * NW + w];
+                    xb += red[3 * NW + w];
+                }
+            }
+            res = zz * A.out_scale + A.out_shift;
+            var = -(xb + mu);
+            if (!isfinite(mu)) singular = true;
+        }
+        if (r == 0) {
+            if (singular) {
+                res = quiet_nan<double>();
+                var = quiet_nan<double>();
+                if (A.n_singular) atomicAdd(A.n_singular, 1);
+            }
+            if (A.z_is_f32) {  // output dtype follows the value dtype
+                static_cast<float*>(A.out)[m] = (float)res;
+                if (A.sigmasq) static_cast<float*>(A.sigmasq)[m] = (float)var;
+            } else {
+                static_cast<double*>(A.out)[m] = res;
+                if (A.sigmasq) static_cast<double*>(A.sigmasq)[m] = var;
+            }
+        }
+        team_barrier();  // the team's shared memory is reused by the next window
+    }
+}
+
+template <int KC>
+int launch_ok_rows(const OkArgs& a, cudaStream_t stream) {
+    constexpr int NW = (KC + 31) / 32;
+    constexpr int TEAMS = NW == 1 ? 4 : 2;  // 128 threads per CTA
+    const size_t smem = TEAMS * ((rows_team_smem<KC>() + 15) & ~size_t(15));
+    CMX_CUDA(cudaFuncSetAttribute(ok_solve_rows_kernel<KC, TEAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long ctas = (a.M + TEAMS - 1) / TEAMS;
+    const long long cap = (long long)sm_count() * 8;
+    if (ctas > cap) ctas = cap;
+    timing_begin(CMX_KERNEL_OK_SOLVE, stream);
+    ok_solve_rows_kernel<KC, TEAMS><<<(unsigned)ctas, TEAMS * NW * 32, smem, stream>>>(a);
+    timing_end(CMX_KERNEL_OK_SOLVE, stream);
+    note_launch();
+    return check_launch();
+}
+
 template <int W, typename V>
 int launch_ok_team(const OkArgs& a, cudaStream_t stream) {
     const int k = a.k;
@@ -465,6 +810,12 @@ int solve_table(const double* s_x, const double* s_y, const V* z, long long n, c
     a.out = out;
     a.sigmasq = sigmasq;
     a.n_singular = n_singular;
+#ifndef CMX_OK_SMEM_ONLY
+    if (k <= 16) return launch_ok_rows<16>(a, stream);
+    if (k <= 32) return launch_ok_rows<32>(a, stream);
+    if (k <= 48) return launch_ok_rows<48>(a, stream);
+    if (k <= 64) return launch_ok_rows<64>(a, stream);
+#endif
     if (k <= 32) return launch_ok<1, V>(a, stream);
     if (k <= 64) return launch_ok_team<2, V>(a, stream);
     return launch_ok_team<4, V>(a, stream);

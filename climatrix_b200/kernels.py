@@ -118,7 +118,34 @@ def reset_launch_count() -> None:
     _lib.load().cmx_reset_launch_count()
 
 
-KERNEL_KNN, KERNEL_IDW_BATCH, KERNEL_OK_SOLVE = 0, 1, 2
+KERNEL_KNN, KERNEL_IDW_BATCH, KERNEL_OK_SOLVE, KERNEL_KNN_BINNED = 0, 1, 2, 3
+
+SEARCH_ALGORITHMS = {"brute": 0, "binned": 1}
+_search = "brute"
+
+
+def set_search(algorithm: str) -> str:
+    """Choose the planar neighbour search for all following calls of this process; returns the previous one.
+
+    ``"brute"`` (default): K1, every (target, sample) pair is evaluated - the brute-force kernel of the
+    north_star.  ``"binned"``: K1c, samples counting-sorted into grid cells, each target scans only the
+    cells its k-th-distance bound touches (the role cKDTree's pruning plays in ``reconstruct/idw.py:155-158``).
+    Both produce identical neighbour tables.
+    """
+    global _search
+    if algorithm not in SEARCH_ALGORITHMS:
+        raise ValueError(f"unknown search algorithm {algorithm!r}; choose from {sorted(SEARCH_ALGORITHMS)}")
+    prev, _search = _search, algorithm
+    return prev
+
+
+def get_search() -> str:
+    return _search
+
+
+def _apply_search(lib) -> None:
+    # the library setting is per thread; the Python setting is per process
+    lib.cmx_set_search(SEARCH_ALGORITHMS[_search])
 
 
 def kernel_timing(enable: bool) -> None:
@@ -161,6 +188,7 @@ def knn(s_lat, s_lon, targets: Targets, k: int, *, return_distance: bool = True)
     Euclidean in the flat (lat, lon) plane, rows ascending by (distance, index).
     """
     lib = _lib.load()
+    _apply_search(lib)
     dev = _require_cuda(targets.lat.device)
     s_lat, s_lon = _as_f64(s_lat, dev), _as_f64(s_lon, dev)
     _check_samples(s_lat, s_lon)
@@ -208,6 +236,7 @@ def idw(s_lat, s_lon, values, targets: Targets, *, k: int = 5, power: float = 2.
     with ``return_neighbours`` also ``(dist, idx)``.
     """
     lib = _lib.load()
+    _apply_search(lib)
     dev = _require_cuda(targets.lat.device)
     if dtype not in (torch.float64, torch.float32):
         raise TypeError("dtype must be torch.float64 or torch.float32")
@@ -330,6 +359,7 @@ def ok_moving_window(s_x, s_y, z, t_x, t_y, grid: bool, *, k: int, variogram_mod
     Grid targets: x = columns (n_x), y = rows (n_y); output (n_y * n_x,).
     """
     lib = _lib.load()
+    _apply_search(lib)
     dev = _require_cuda(s_x.device if isinstance(s_x, torch.Tensor) else None)
     s_x, s_y = _as_f64(s_x, dev), _as_f64(s_y, dev)
     t_x, t_y = _as_f64(t_x, dev), _as_f64(t_y, dev)

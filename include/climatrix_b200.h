@@ -209,6 +209,23 @@ int cmx_ok_solve_f32(const double* s_x, const double* s_y, const float* z, int64
 /* total scratch for cmx_ok_mw_* (includes the kNN scratch) */
 size_t cmx_ok_workspace_bytes(int k, int64_t n_targets);
 
+/* ---- neighbour-search algorithm ----
+ *
+ * Every entry point that searches planar neighbours (cmx_knn, cmx_idw_*, cmx_ok_mw_*) uses the algorithm
+ * selected here for the calling thread.  Both return the same neighbour tables (exact float64 distances,
+ * ties by sample index); they differ only in the work done:
+ *   CMX_SEARCH_BRUTE  (default) K1: every (target, sample) pair is evaluated (north_star's brute-force kernel).
+ *   CMX_SEARCH_BINNED K1c: samples are counting-sorted into the cells of the seed grid and each target scans
+ *                     only the cells that intersect the disc of its k-th-distance bound - the device counterpart
+ *                     of cKDTree's pruning (reference: reconstruct/idw.py:155-158).  Needs 20 B per sample of
+ *                     the ordinary kNN workspace; if that does not fit, the call uses K1.
+ * cmx_set_search returns the previous setting, or CMX_ERR_BAD_ARG.
+ */
+#define CMX_SEARCH_BRUTE 0
+#define CMX_SEARCH_BINNED 1
+int cmx_set_search(int algorithm);
+int cmx_get_search(void);
+
 /* ---- instrumentation ---- */
 
 /* Kernels launched by this library on the calling thread since the last reset. */
@@ -218,13 +235,15 @@ void cmx_reset_launch_count(void);
 /*
  * Optional per-kernel device timing (bench.py's roofline): when enabled, the library brackets
  * its two hot kernels with CUDA events on the launching stream.
- *   kind 0 = K1 neighbour search (knn_kernel), kind 1 = K2 batched IDW apply, kind 2 = K4 kriging solve.
+ *   kind 0 = K1 neighbour search (knn_kernel), kind 1 = K2 batched IDW apply, kind 2 = K4 kriging solve,
+ *   kind 3 = K1c cell-binned neighbour search (scatter + knn_binned_kernel).
  * cmx_timing_read synchronises on the recorded events and returns the accumulated
  * milliseconds and the number of launches since the last cmx_timing_reset.
  */
 #define CMX_KERNEL_KNN 0
 #define CMX_KERNEL_IDW_BATCH 1
 #define CMX_KERNEL_OK_SOLVE 2
+#define CMX_KERNEL_KNN_BINNED 3
 void cmx_timing_enable(int on);
 void cmx_timing_reset(void);
 int cmx_timing_read(int kind, double* total_ms, int64_t* launches);

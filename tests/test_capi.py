@@ -76,3 +76,22 @@ def test_check_maps_codes_to_python_exceptions():
     with pytest.raises(RuntimeError):
         _lib.check(_lib.ERR_CUDA, "x")
     _lib.check(0)
+
+
+def test_search_selection_is_host_state():
+    lib = _lib.load()
+    assert lib.cmx_get_search() == 0  # brute force is the default
+    assert lib.cmx_set_search(1) == 0
+    assert lib.cmx_get_search() == 1
+    assert lib.cmx_set_search(7) == _lib.ERR_BAD_ARG
+    assert lib.cmx_get_search() == 1
+    assert lib.cmx_set_search(0) == 1
+    import climatrix_b200 as cm
+
+    assert cm.get_search() == "brute"
+    assert cm.set_search("binned") == "brute"
+    assert cm.set_search("brute") == "binned"
+    import pytest
+
+    with pytest.raises(ValueError):
+        cm.set_search("kd-tree")

@@ -29,6 +29,15 @@ OK_RTOL = 1e-4
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True, params=["brute", "binned"])
+def search(request):
+    """Every test of this module runs once per neighbour-search algorithm (K1 brute force, K1c cell-binned):
+    both must reproduce the oracle bit for bit."""
+    prev = K.set_search(request.param)
+    yield request.param
+    K.set_search(prev)
+
+
 def _samples(n, seed, lat=(-90, 90), lon=(-180, 180)):
     rng = np.random.default_rng(seed)
     la, lo = rng.uniform(*lat, n), rng.uniform(*lon, n)

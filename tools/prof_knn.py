@@ -3,6 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from climatrix_b200 import kernels as K
+K.set_search(os.environ.get('CMX_SEARCH', 'brute'))
 N, nlat, nlon, k = (int(a) for a in sys.argv[1:5])
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 1
 rng = np.random.default_rng(7)

@@ -4,6 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from scipy.spatial import cKDTree
 from climatrix_b200 import kernels as K
+K.set_search(os.environ.get('CMX_SEARCH', 'brute'))
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 dev = "cuda:0"
 bad = 0
