@@ -794,6 +794,38 @@ __global__ void bin_scatter_kernel(const double* __restrict__ sa, const double* 
     }
 }
 
+// seed_bound_d2 evaluated by a whole warp for one target: lane l tests box half-width w_l (0..8, then doubling)
+// in one round, the first lane whose box holds >= k samples wins; the plus-shaped refinement tests 32 arm
+// lengths in a second round and the three far-corner distances are evaluated by lanes 0..2 at once.
+// Same family of rigorous bounds as seed_bound_d2 (any region with >= k samples bounds the k-th distance).
+__device__ __forceinline__ double seed_bound_d2_warp(const SeedGrid& s, const int* __restrict__ sat, double ta,
+                                                     double tb, int k, int lane) {
+    const int ia = seed_cell(ta, s.a0, s.inv_h, s.ga), ib = seed_cell(tb, s.b0, s.inv_h, s.gb);
+    const int wl = lane <= 8 ? lane : (lane < 30 ? 8 << (lane - 8) : 0x3fffffff);
+    const unsigned okb = __ballot_sync(kFull, seed_box_count(s, sat, ia - wl, ia + wl, ib - wl, ib + wl) >= k);
+    if (okb == 0u) return CMX_INF;  // fewer than k finite samples in total
+    const int w = __shfl_sync(kFull, wl, __ffs(okb) - 1);
+    int A = w, B = w;
+    unsigned okp = 0u;
+    if (w >= 2 && w <= 64) {
+        // plus shape: [ia-A, ia+A] x [ib-B, ib+B]  U  [ia-B, ia+B] x [ib-A, ib+A],  B ~ 0.6 A
+        const int Al = w + lane, Bl = (3 * Al + 2) / 5;
+        const int cnt = seed_box_count(s, sat, ia - Al, ia + Al, ib - Bl, ib + Bl) +
+                        seed_box_count(s, sat, ia - Bl, ia + Bl, ib - Al, ib + Al) -
+                        seed_box_count(s, sat, ia - Bl, ia + Bl, ib - Bl, ib + Bl);
+        okp = __ballot_sync(kFull, cnt >= k && lane <= (w >> 1) + 1);
+        if (okp) {
+            A = w + __ffs(okp) - 1;
+            B = (3 * A + 2) / 5;
+        }
+    }
+    // lane 0: the square; lanes 1, 2: the two rectangles of the plus (both inside the disc through their far corners)
+    const int ha = lane == 0 ? w : (lane == 1 ? A : B), hb = lane == 0 ? w : (lane == 1 ? B : A);
+    const double far2 = seed_box_far2(s, ta, tb, ia - ha, ia + ha, ib - hb, ib + hb);
+    const double f0 = __shfl_sync(kFull, far2, 0), f1 = __shfl_sync(kFull, far2, 1), f2 = __shfl_sync(kFull, far2, 2);
+    return okp ? fmin(f0, fmax(f1, f2)) : f0;
+}
+
 // One warp per target.  The seed bound D2 >= (k-th nearest distance)^2 is rigorous, so every one of the k
 // nearest samples lies in the cells that the square [t - D, t + D]^2 touches; in the sorted order each cell
 // row of that square is one contiguous segment.  Lanes own one cell row each to look the segments up, the
@@ -828,8 +860,9 @@ __global__ void __launch_bounds__(256) knn_binned_kernel(const __grid_constant__
         }
         int ra0 = 0, ra1 = -1, cb0 = 0, cb1 = -1;
         double kth = CMX_INF;
+        bool empty = true;
         if (s.valid) {
-            kth = seed_bound_d2(s, sat, ta, tb, k);
+            kth = seed_bound_d2_warp(s, sat, ta, tb, k, lane);
             if (kth < CMX_INF) {
                 const double D = sqrt(kth) * (1.0 + 1e-12);
                 ra0 = seed_cell(ta - D, s.a0, s.inv_h, s.ga);
@@ -881,7 +914,13 @@ __global__ void __launch_bounds__(256) knn_binned_kernel(const __grid_constant__
                     double cd = c ? d2 : CMX_INF;
                     int ci = c ? a.bin_idx[p] : INT_MAX;
                     warp_sort32(cd, ci, lane);
-                    merge_sorted32<E>(ld, li, cd, ci, lane);
+                    if (empty) {  // first candidates of this target: the sorted chunk is the list
+                        ld[0] = cd;
+                        li[0] = ci;
+                        empty = false;
+                    } else {
+                        merge_sorted32<E>(ld, li, cd, ci, lane);
+                    }
                     double sel = ld[0];
 #pragma unroll
                     for (int e = 1; e < E; ++e)
