@@ -120,6 +120,284 @@ __global__ void __launch_bounds__(BW_THREADS) idw_batch_kernel(
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K2, neighbour-sharing variant (default for k <= 32).
+//
+// Adjacent grid targets share most of their neighbours (a run of 16 targets touches ~50-100 distinct
+// samples, not 16 * 32).  The kernel above fetches every (target, neighbour) value separately and is
+// bound by those gathers (ncu: LSU pipe 46 %, long-scoreboard stalls on L1 misses).  Here a CTA of 16
+// consecutive targets first de-duplicates its neighbour indices in shared memory (open-addressing hash
+// on the sample index; slots are numbered by FIRST OCCURRENCE in (target, rank) order through a block
+// prefix sum, so the summation order - and with it every output bit - is deterministic), scatters the
+// normalised weights into a dense W[union][16] table and records per warp a bit mask of the union
+// entries its 4 targets use.  In the sweep a warp walks that mask: ONE value load per union sample and
+// batch element feeds 4 targets (W row read by two 16-byte broadcast loads), two batch elements per
+// thread, i.e. 2 global loads per 8 fma instead of 8 per 8.  CTAs whose union exceeds the table, values
+// with non-finite entries and k > 32 take the per-target loop (same results).
+// ------------------------------------------------------------------------------------------
+constexpr int UT = 16;            // targets per CTA
+constexpr int UWARPS = 4;         // 4 targets per warp
+constexpr int UTHREADS = UWARPS * 32;
+constexpr int UMAX = 128;         // union capacity
+constexpr int UHS = 1024;         // hash slots (<= 512 entries)
+constexpr int UK = 32;            // largest k for the shared sweep
+
+template <typename V, int TT>
+__device__ __forceinline__ void union_sweep_chunk(const unsigned char* s_ulist, int n_list,
+                                                  const unsigned long long* s_uoff, const double* s_W,
+                                                  const double* s_wsum, V* s_tile, const V* vals, long long t0,
+                                                  long long n_batch, long long stride_t, int warp, int lane) {
+    const char* base[TT];
+#pragma unroll
+    for (int tt = 0; tt < TT; ++tt) {
+        const long long t = t0 + tt * 32 + lane;
+        base[tt] = reinterpret_cast<const char*>(vals) + (t < n_batch ? t : 0) * stride_t * (long long)sizeof(V);
+    }
+    double acc[4][TT];
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int tt = 0; tt < TT; ++tt) acc[g][tt] = 0.0;
+    // the list is padded to a multiple of 4 with the all-zero row UMAX: four union samples (8 loads) in flight
+#pragma unroll 1
+    for (int j = 0; j < n_list; j += 4) {
+        const unsigned u4 = *reinterpret_cast<const unsigned*>(s_ulist + warp * (UMAX + 4) + j);
+        double v[4][TT];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const unsigned long long off = s_uoff[(u4 >> (8 * q)) & 0xffu];
+#pragma unroll
+            for (int tt = 0; tt < TT; ++tt) v[q][tt] = (double)*reinterpret_cast<const V*>(base[tt] + off);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int u = (u4 >> (8 * q)) & 0xffu;
+            const double2 w01 = *reinterpret_cast<const double2*>(s_W + u * UT + warp * 4);
+            const double2 w23 = *reinterpret_cast<const double2*>(s_W + u * UT + warp * 4 + 2);
+#pragma unroll
+            for (int tt = 0; tt < TT; ++tt) {
+                acc[0][tt] = fma(w01.x, v[q][tt], acc[0][tt]);
+                acc[1][tt] = fma(w01.y, v[q][tt], acc[1][tt]);
+                acc[2][tt] = fma(w23.x, v[q][tt], acc[2][tt]);
+                acc[3][tt] = fma(w23.y, v[q][tt], acc[3][tt]);
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int tt = 0; tt < TT; ++tt)
+            s_tile[(tt * 32 + lane) * (UT + 1) + warp * 4 + g] = (V)(acc[g][tt] / s_wsum[warp * 4 + g]);
+}
+
+template <typename V>
+__global__ void __launch_bounds__(UTHREADS, 5) idw_batch_union_kernel(
+    const int* __restrict__ idx, const double* __restrict__ dd, int dist_is_squared, long long M, int k_table,
+    int k_use, int k_min, double power, const V* __restrict__ vals, long long n_samples, long long n_batch,
+    long long stride_t, long long stride_i, const int* __restrict__ nonfinite_flag, V* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    NbrEntry* s_ent = reinterpret_cast<NbrEntry*>(smem_raw);                       // [UT][k_use]
+    double* s_W = reinterpret_cast<double*>(s_ent + UT * k_use);                   // [UMAX + 1][UT], row UMAX stays zero
+    unsigned long long* s_uoff = reinterpret_cast<unsigned long long*>(s_W + (UMAX + 1) * UT);  // [UMAX + 1]
+    double* s_wsum = reinterpret_cast<double*>(s_uoff + UMAX + 1);                 // [UT]
+    // the output tile of the sweep reuses the hash storage of the set-up
+    V* s_tile = reinterpret_cast<V*>(s_wsum + UT);                                 // [64][UT + 1]   (10 KB region)
+    int* s_key = reinterpret_cast<int*>(s_wsum + UT);                              // [UT * UK] sample index
+    int* s_hkey = s_key + UT * UK;                                                 // [UHS]
+    int* s_hmin = s_hkey + UHS;                                                    // [UHS]
+    unsigned (*s_mask)[4] = reinterpret_cast<unsigned (*)[4]>(s_hmin + UHS);       // [UWARPS][4]
+    int* s_scan = reinterpret_cast<int*>(s_mask + UWARPS);                         // [UWARPS + 1]
+    unsigned char* s_hval = reinterpret_cast<unsigned char*>(s_scan + UWARPS + 1 + 3);  // [UHS]
+    unsigned char* s_ulist = s_hval + UHS;                                         // [UWARPS][UMAX + 4], 4-byte aligned rows
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long m0 = (long long)blockIdx.x * UT;
+    const bool check = nonfinite_flag ? *nonfinite_flag != 0 : true;
+    const bool shared_sweep = !check && k_use <= UK;
+
+    // ---- weights, once per target (idw.py:163-165) ----
+    for (int tl = warp; tl < UT; tl += UWARPS) {
+        const long long m = m0 + tl;
+        double wsum = 0.0;
+        for (int j = lane; j < k_use; j += 32) {
+            double w = 0.0;
+            long long id = 0;
+            if (m < M) {
+                const double d = dd[m * k_table + j];
+                id = idx[m * k_table + j];
+                if (id >= 0 && id < n_samples)  // the (inf, INT_MAX) sentinel of a short neighbour list carries no weight
+                    w = dist_is_squared ? idw_raw_weight(d, power) : idw_weight_from_dist(d, power);
+                else
+                    id = 0;
+            }
+            s_ent[tl * k_use + j].w = w;
+            s_ent[tl * k_use + j].off = (unsigned long long)(id * stride_i) * sizeof(V);
+            if (shared_sweep) s_key[tl * k_use + j] = (int)id;
+            wsum += w;
+        }
+        wsum = warp_sum(wsum);
+        __syncwarp();
+        double wn = 0.0;
+        for (int j = lane; j < k_use; j += 32) {
+            const double w = s_ent[tl * k_use + j].w / wsum;
+            s_ent[tl * k_use + j].w = w;
+            wn += w;
+        }
+        wn = warp_sum(wn);
+        if (lane == 0) s_wsum[tl] = wn;
+    }
+    bool use_union = false;
+    if (shared_sweep) {
+        for (int i = tid; i < UHS; i += UTHREADS) {
+            s_hkey[i] = -1;
+            s_hmin[i] = 0x7fffffff;
+        }
+        for (int i = tid; i < (UMAX + 1) * UT; i += UTHREADS) s_W[i] = 0.0;
+        if (tid == 0) s_uoff[UMAX] = 0ull;
+        if (tid < UWARPS * 4) (&s_mask[0][0])[tid] = 0u;
+        __syncthreads();
+        // ---- de-duplicate: entries e = target * k + rank, EPT consecutive entries per thread ----
+        constexpr int EPT = UT * UK / UTHREADS;  // 4
+        const int n_ent = UT * k_use;
+        int myh[EPT];
+        bool valid[EPT];
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const int e = tid * EPT + i;
+            valid[i] = e < n_ent && s_ent[e].w > 0.0;
+            myh[i] = 0;
+            if (valid[i]) {
+                const int key = s_key[e];
+                unsigned h = ((unsigned)key * 2654435761u) >> 22;  // 10 bits
+                for (;;) {
+                    const int old = atomicCAS(&s_hkey[h], -1, key);
+                    if (old == -1 || old == key) break;
+                    h = (h + 1) & (UHS - 1);
+                }
+                atomicMin(&s_hmin[h], e);
+                myh[i] = (int)h;
+            }
+        }
+        __syncthreads();
+        int lead = 0;
+        bool is_lead[EPT];
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            is_lead[i] = valid[i] && s_hmin[myh[i]] == tid * EPT + i;
+            lead += is_lead[i];
+        }
+        int incl = lead;  // block prefix sum of the leader counts, in entry order
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        int base = incl - lead, total = 0;
+#pragma unroll
+        for (int w = 0; w < UWARPS; ++w) {
+            if (w < warp) base += s_scan[w];
+            total += s_scan[w];
+        }
+        use_union = total <= UMAX;  // CTA-uniform
+        if (use_union) {
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+                if (is_lead[i]) {
+                    s_hval[myh[i]] = (unsigned char)base;
+                    s_uoff[base] = s_ent[tid * EPT + i].off;
+                    ++base;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+                if (valid[i]) {
+                    const int e = tid * EPT + i, g = e / k_use;
+                    const int u = s_hval[myh[i]];
+                    s_W[u * UT + g] = s_ent[e].w;
+                    atomicOr(&s_mask[g >> 2][u >> 5], 1u << (u & 31));
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    if (use_union) {
+        // ---- per warp: compact list of the union entries its 4 targets use, padded with the zero row ----
+        int n_list = 0;
+        for (int word = 0; word < UMAX / 32; ++word) {
+            const unsigned bits = s_mask[warp][word];
+            if ((bits >> lane) & 1u) s_ulist[warp * (UMAX + 4) + n_list + __popc(bits & ((1u << lane) - 1u))] = (unsigned char)(word * 32 + lane);
+            n_list += __popc(bits);
+        }
+        if (lane < 4) s_ulist[warp * (UMAX + 4) + n_list + lane] = (unsigned char)UMAX;
+        n_list = (n_list + 3) & ~3;
+        __syncthreads();  // lists visible; the hash storage may now be reused as the output tile
+        // ---- shared sweep: 64 batch elements per pass (two per thread), 32 in a short tail ----
+        for (long long t0 = 0; t0 < n_batch; t0 += 64) {
+            const bool two = n_batch - t0 > 32;
+            if (two)
+                union_sweep_chunk<V, 2>(s_ulist, n_list, s_uoff, s_W, s_wsum, s_tile, vals, t0, n_batch, stride_t, warp, lane);
+            else
+                union_sweep_chunk<V, 1>(s_ulist, n_list, s_uoff, s_W, s_wsum, s_tile, vals, t0, n_batch, stride_t, warp, lane);
+            __syncthreads();
+            // coalesced stores: a half-warp writes one 16-target row segment
+            const int rows = two ? 64 : 32;
+            for (int tr = warp * 2 + (lane >> 4); tr < rows; tr += UWARPS * 2) {
+                const long long tt = t0 + tr;
+                const long long m = m0 + (lane & 15);
+                if (tt < n_batch && m < M) out[tt * M + m] = s_tile[tr * (UT + 1) + (lane & 15)];
+            }
+            __syncthreads();
+        }
+        return;
+    }
+
+    // ---- per-target sweep (non-finite values, k > 32, or a union that does not fit) ----
+    for (long long t0 = 0; t0 < n_batch; t0 += 32) {
+        const long long t = t0 + lane;
+        const bool tin = t < n_batch;
+        const char* lane_base = reinterpret_cast<const char*>(vals) + (tin ? t : 0) * stride_t * (long long)sizeof(V);
+        for (int tl = warp; tl < UT; tl += UWARPS) {
+            const NbrEntry* e = s_ent + tl * k_use;
+            V r;
+            if (!check) {
+                double acc = 0.0;
+#pragma unroll 8
+                for (int j = 0; j < k_use; ++j) {
+                    const NbrEntry q = e[j];
+                    acc = fma(q.w, (double)*reinterpret_cast<const V*>(lane_base + q.off), acc);
+                }
+                r = (V)(acc / s_wsum[tl]);
+            } else {
+                double num = 0.0, den = 0.0;
+                int fin = 0;
+#pragma unroll 4
+                for (int j = 0; j < k_use; ++j) {
+                    const NbrEntry q = e[j];
+                    const double v = (double)*reinterpret_cast<const V*>(lane_base + q.off);
+                    if (isfinite(v) && q.w > 0.0) {
+                        num = fma(q.w, v, num);
+                        den += q.w;
+                        ++fin;
+                    }
+                }
+                r = (fin < k_min || den == 0.0) ? quiet_nan<V>() : (V)(num / den);
+            }
+            s_tile[lane * (UT + 1) + tl] = r;  // [t_local][target_local]
+        }
+        __syncthreads();
+        for (int tr = warp * 2 + (lane >> 4); tr < 32; tr += UWARPS * 2) {
+            const long long tt = t0 + tr;
+            const long long m = m0 + (lane & 15);
+            if (tt < n_batch && m < M) out[tt * M + m] = s_tile[tr * (UT + 1) + (lane & 15)];
+        }
+        __syncthreads();
+    }
+}
+
 // single slice from a table: one warp per target (HPO inner loop, small problems)
 template <typename V>
 __global__ void idw_apply_single_kernel(const int* __restrict__ idx, const double* __restrict__ dd,
@@ -196,14 +474,32 @@ int idw_from_table(const int* idx, const double* dd, int dist_is_squared, long l
         flag_nonfinite_kernel<V><<<fblocks, 256, 0, stream>>>(vals, n_samples * n_batch, flag_scratch);
         note_launch();
     }
-    const size_t smem = (size_t)BW_TARGETS * k_use * sizeof(NbrEntry) + BW_TARGETS * sizeof(double) + 32 * 33 * sizeof(V);
-    const long long blocks = (M + BW_TARGETS - 1) / BW_TARGETS;
-    if (smem > 48 * 1024)
-        CMX_CUDA(cudaFuncSetAttribute(idw_batch_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    timing_begin(CMX_KERNEL_IDW_BATCH, stream);
-    idw_batch_kernel<V><<<(unsigned)blocks, BW_THREADS, smem, stream>>>(idx, dd, dist_is_squared, M, k_table, k_use,
-                                                                       k_min, power, vals, n_samples, n_batch,
-                                                                       stride_t, stride_i, flag_scratch, out);
+#ifndef CMX_K2_UNION_MIN_BATCH
+#define CMX_K2_UNION_MIN_BATCH 128
+#endif
+    if (n_batch < CMX_K2_UNION_MIN_BATCH || k_use > UK) {  // short batches: the set-up of the shared sweep does not pay
+        const size_t smem = (size_t)BW_TARGETS * k_use * sizeof(NbrEntry) + BW_TARGETS * sizeof(double) + 32 * 33 * sizeof(V);
+        const long long blocks = (M + BW_TARGETS - 1) / BW_TARGETS;
+        if (smem > 48 * 1024)
+            CMX_CUDA(cudaFuncSetAttribute(idw_batch_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        timing_begin(CMX_KERNEL_IDW_BATCH, stream);
+        idw_batch_kernel<V><<<(unsigned)blocks, BW_THREADS, smem, stream>>>(idx, dd, dist_is_squared, M, k_table, k_use,
+                                                                           k_min, power, vals, n_samples, n_batch,
+                                                                           stride_t, stride_i, flag_scratch, out);
+    } else {
+        const size_t smem = (size_t)UT * k_use * sizeof(NbrEntry) + (size_t)(UMAX + 1) * UT * sizeof(double) +
+                            (UMAX + 1) * sizeof(unsigned long long) + UT * sizeof(double) +
+                            (size_t)UT * UK * sizeof(int) + 2 * UHS * sizeof(int) + UWARPS * 4 * sizeof(unsigned) +
+                            (UWARPS + 1 + 3) * sizeof(int) + UHS + UWARPS * (UMAX + 4) + 64;
+        static_assert((size_t)UT * UK * sizeof(int) + 2 * UHS * sizeof(int) >= 64 * (UT + 1) * sizeof(double),
+                      "output tile must fit in the hash storage it reuses");
+        const long long blocks = (M + UT - 1) / UT;
+        CMX_CUDA(cudaFuncSetAttribute(idw_batch_union_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        timing_begin(CMX_KERNEL_IDW_BATCH, stream);
+        idw_batch_union_kernel<V><<<(unsigned)blocks, UTHREADS, smem, stream>>>(idx, dd, dist_is_squared, M, k_table,
+                                                                               k_use, k_min, power, vals, n_samples,
+                                                                               n_batch, stride_t, stride_i, flag_scratch, out);
+    }
     timing_end(CMX_KERNEL_IDW_BATCH, stream);
     note_launch();
     return check_launch();
