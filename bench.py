@@ -203,6 +203,9 @@ def main():
     ap.add_argument("--search", default="brute", choices=["brute", "binned"],
                     help="neighbour search of the headline numbers: K1 brute force (north_star) or K1c cell-binned")
     ap.add_argument("--no-binned", action="store_true", help="skip the extra K1c (binned search) measurement")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the ranks' bands become the full field on every rank: stored by the weighting kernel "
+                         "itself into all ranks' buffers over NVLink peer memory (default), or an NCCL all-gather after it")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -274,7 +277,29 @@ def main():
         # variogram fit is part of the path: do it once per step (K3 + host fit) like the reference constructor
         pass
 
+    peer = None
+    if world > 1 and method == "idw" and t > 1 and args.gather == "peer":
+        from climatrix_b200.sharding import PeerGather
+        try:
+            peer = PeerGather.get(t, n_lat, n_lon, tdtype, dev)
+        except Exception as exc:  # noqa: BLE001  (no peer-mapped memory on this box: NCCL gather instead)
+            print(f"[bench] symmetric memory unavailable ({type(exc).__name__}: {exc}); using the NCCL gather", file=sys.stderr)
+            peer = None
+        ok = torch.tensor([1 if peer is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            peer = None
+    config["gather"] = ("peer stores from the weighting kernel (symmetric memory over NVLink)" if peer is not None
+                        else ("NCCL all-gather" if world > 1 else "none (1 rank)"))
+
     def step():
+        if method == "idw" and peer is not None:
+            peer.begin()
+            if r1 > r0:
+                tg = K.Targets(t_lat_d[r0:r1].contiguous(), t_lon_d, True)
+                K.idw(s_lat, s_lon, vals, tg, k=k, power=2.0, k_min=2, dtype=tdtype, layout="sample_major",
+                      peer_out=peer.peer_out(r0))
+            return peer.finish()
         if method == "idw":
             def compute(a, b):
                 if b == a:
@@ -429,7 +454,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "output_values_per_s": value * t, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "search": args.search, "binned_search": binned,
-            "notes": "fp32 distance filter + exact float64 re-rank; values/output float64; NCCL all-gather of output slabs inside the step for N>1",
+            "notes": "fp32 distance filter + exact float64 re-rank; values/output float64; N>1: every rank ends the step with the full field (config.gather)",
         }
         print(json.dumps(line), flush=True)
     if world > 1:

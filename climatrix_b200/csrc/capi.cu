@@ -9,10 +9,16 @@ namespace {
 thread_local long long g_launches = 0;
 thread_local char g_cuda_err[256] = "";
 thread_local int g_search = CMX_SEARCH_BRUTE;
+thread_local PeerOut g_peer_out = {};
 }  // namespace
 
 void note_launch() { ++g_launches; }
 int search_algorithm() { return g_search; }
+PeerOut take_peer_out() {
+    const PeerOut p = g_peer_out;
+    g_peer_out.n = 0;
+    return p;
+}
 
 int cuda_fail(cudaError_t e) {
     snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
@@ -112,6 +118,23 @@ int cmx_set_search(int algorithm) {
     return prev;
 }
 int cmx_get_search(void) { return cmx::g_search; }
+
+int cmx_set_output_peers(void* const* peer_out, int n_peers, int64_t m_total, int64_t m_offset) {
+    if (n_peers == 0) {
+        cmx::g_peer_out.n = 0;
+        return CMX_OK;
+    }
+    if (!peer_out || n_peers < 0 || n_peers > CMX_MAX_PEERS || m_total < 0 || m_offset < 0 || m_offset > m_total)
+        return CMX_ERR_BAD_ARG;
+    for (int i = 0; i < n_peers; ++i) {
+        if (!peer_out[i]) return CMX_ERR_BAD_ARG;
+        cmx::g_peer_out.base[i] = peer_out[i];
+    }
+    cmx::g_peer_out.n = n_peers;
+    cmx::g_peer_out.m_total = m_total;
+    cmx::g_peer_out.m_off = m_offset;
+    return CMX_OK;
+}
 
 int64_t cmx_launch_count(void) { return cmx::g_launches; }
 void cmx_reset_launch_count(void) { cmx::g_launches = 0; }

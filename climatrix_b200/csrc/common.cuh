@@ -14,6 +14,15 @@ constexpr unsigned kFull = 0xffffffffu;
 // ---- host-side bookkeeping (thread-local) ---------------------------------
 void note_launch();                 // ++launch counter
 int search_algorithm();             // CMX_SEARCH_* selected by cmx_set_search on this thread
+
+// Output redirection of the batched IDW kernels (cmx_set_output_peers): the same row segment is stored into the
+// buffers of up to CMX_MAX_PEERS devices (this one included) at column offset m_off of rows m_total wide.
+struct PeerOut {
+    void* base[CMX_MAX_PEERS];
+    int n;  // 0: plain output
+    long long m_total, m_off;
+};
+PeerOut take_peer_out();            // returns the pending redirection of this thread and clears it
 int cuda_fail(cudaError_t e);       // records text, returns CMX_ERR_CUDA
 int check_launch();                 // cudaGetLastError() -> CMX_OK / CMX_ERR_CUDA
 int sm_count();                     // SMs of the current device (cached)

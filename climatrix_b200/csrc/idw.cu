@@ -34,7 +34,7 @@ template <typename V>
 __global__ void __launch_bounds__(BW_THREADS) idw_batch_kernel(
     const int* __restrict__ idx, const double* __restrict__ dd, int dist_is_squared, long long M, int k_table,
     int k_use, int k_min, double power, const V* __restrict__ vals, long long n_samples, long long n_batch,
-    long long stride_t, long long stride_i, const int* __restrict__ nonfinite_flag, V* __restrict__ out) {
+    long long stride_t, long long stride_i, const int* __restrict__ nonfinite_flag, const PeerOut po) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NbrEntry* s_ent = reinterpret_cast<NbrEntry*>(smem_raw);               // [32][k_use]
     double* s_wsum = reinterpret_cast<double*>(s_ent + BW_TARGETS * k_use);  // [32]
@@ -114,7 +114,10 @@ __global__ void __launch_bounds__(BW_THREADS) idw_batch_kernel(
         for (int tr = warp; tr < 32; tr += BW_WARPS) {
             const long long tt = t0 + tr;
             const long long m = m0 + lane;
-            if (tt < n_batch && m < M) out[tt * M + m] = s_tile[tr * 33 + lane];
+            if (tt < n_batch && m < M) {
+                const V r = s_tile[tr * 33 + lane];
+                for (int p = 0; p < po.n; ++p) static_cast<V*>(po.base[p])[tt * po.m_total + po.m_off + m] = r;
+            }
         }
         __syncthreads();
     }
@@ -194,7 +197,7 @@ template <typename V>
 __global__ void __launch_bounds__(UTHREADS, 5) idw_batch_union_kernel(
     const int* __restrict__ idx, const double* __restrict__ dd, int dist_is_squared, long long M, int k_table,
     int k_use, int k_min, double power, const V* __restrict__ vals, long long n_samples, long long n_batch,
-    long long stride_t, long long stride_i, const int* __restrict__ nonfinite_flag, V* __restrict__ out) {
+    long long stride_t, long long stride_i, const int* __restrict__ nonfinite_flag, const PeerOut po) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NbrEntry* s_ent = reinterpret_cast<NbrEntry*>(smem_raw);                       // [UT][k_use]
     double* s_W = reinterpret_cast<double*>(s_ent + UT * k_use);                   // [UMAX + 1][UT], row UMAX stays zero
@@ -348,7 +351,10 @@ __global__ void __launch_bounds__(UTHREADS, 5) idw_batch_union_kernel(
             for (int tr = warp * 2 + (lane >> 4); tr < rows; tr += UWARPS * 2) {
                 const long long tt = t0 + tr;
                 const long long m = m0 + (lane & 15);
-                if (tt < n_batch && m < M) out[tt * M + m] = s_tile[tr * (UT + 1) + (lane & 15)];
+                if (tt < n_batch && m < M) {
+                    const V r = s_tile[tr * (UT + 1) + (lane & 15)];
+                    for (int p = 0; p < po.n; ++p) static_cast<V*>(po.base[p])[tt * po.m_total + po.m_off + m] = r;
+                }
             }
             __syncthreads();
         }
@@ -392,7 +398,10 @@ __global__ void __launch_bounds__(UTHREADS, 5) idw_batch_union_kernel(
         for (int tr = warp * 2 + (lane >> 4); tr < 32; tr += UWARPS * 2) {
             const long long tt = t0 + tr;
             const long long m = m0 + (lane & 15);
-            if (tt < n_batch && m < M) out[tt * M + m] = s_tile[tr * (UT + 1) + (lane & 15)];
+            if (tt < n_batch && m < M) {
+                const V r = s_tile[tr * (UT + 1) + (lane & 15)];
+                for (int p = 0; p < po.n; ++p) static_cast<V*>(po.base[p])[tt * po.m_total + po.m_off + m] = r;
+            }
         }
         __syncthreads();
     }
@@ -455,8 +464,15 @@ __global__ void flag_nonfinite_kernel(const V* __restrict__ v, long long count, 
 template <typename V>
 int idw_from_table(const int* idx, const double* dd, int dist_is_squared, long long M, int k_table, int k_use,
                    int k_min, double power, const V* vals, long long n_samples, long long n_batch, int layout,
-                   V* out, int* flag_scratch, cudaStream_t stream) {
+                   V* out, int* flag_scratch, cudaStream_t stream, PeerOut po = PeerOut{}) {
     if (M == 0 || n_batch == 0) return CMX_OK;
+    if (po.n > 0 && n_batch == 1) return CMX_ERR_UNSUPPORTED;
+    if (po.n == 0) {  // plain output
+        po.base[0] = out;
+        po.n = 1;
+        po.m_total = M;
+        po.m_off = 0;
+    }
     const long long stride_t = layout == CMX_LAYOUT_SAMPLE_MAJOR ? 1 : n_samples;
     const long long stride_i = layout == CMX_LAYOUT_SAMPLE_MAJOR ? n_batch : 1;
     if (n_batch == 1) {
@@ -485,7 +501,7 @@ int idw_from_table(const int* idx, const double* dd, int dist_is_squared, long l
         timing_begin(CMX_KERNEL_IDW_BATCH, stream);
         idw_batch_kernel<V><<<(unsigned)blocks, BW_THREADS, smem, stream>>>(idx, dd, dist_is_squared, M, k_table, k_use,
                                                                            k_min, power, vals, n_samples, n_batch,
-                                                                           stride_t, stride_i, flag_scratch, out);
+                                                                           stride_t, stride_i, flag_scratch, po);
     } else {
         const size_t smem = (size_t)UT * k_use * sizeof(NbrEntry) + (size_t)(UMAX + 1) * UT * sizeof(double) +
                             (UMAX + 1) * sizeof(unsigned long long) + UT * sizeof(double) +
@@ -498,7 +514,7 @@ int idw_from_table(const int* idx, const double* dd, int dist_is_squared, long l
         timing_begin(CMX_KERNEL_IDW_BATCH, stream);
         idw_batch_union_kernel<V><<<(unsigned)blocks, UTHREADS, smem, stream>>>(idx, dd, dist_is_squared, M, k_table,
                                                                                k_use, k_min, power, vals, n_samples,
-                                                                               n_batch, stride_t, stride_i, flag_scratch, out);
+                                                                               n_batch, stride_t, stride_i, flag_scratch, po);
     }
     timing_end(CMX_KERNEL_IDW_BATCH, stream);
     note_launch();
@@ -511,7 +527,9 @@ int idw_entry(const double* s_lat, const double* s_lon, int64_t n, const V* vals
               double power, V* out, int32_t* idx_out, double* dist_out, void* workspace, size_t workspace_bytes,
               void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const PeerOut po = take_peer_out();  // consumed by this call, whatever happens next
     if (!vals || !out || n_batch < 1 || k_min < 1) return CMX_ERR_BAD_ARG;
+    if (po.n > 0 && n_batch == 1) return CMX_ERR_UNSUPPORTED;
     if (layout != CMX_LAYOUT_BATCH_MAJOR && layout != CMX_LAYOUT_SAMPLE_MAJOR) return CMX_ERR_BAD_ARG;
     if (n_lat < 0 || n_lon < 0) return CMX_ERR_BAD_ARG;
     const long long M = grid ? (long long)n_lat * n_lon : (long long)n_lat;
@@ -556,13 +574,14 @@ int idw_entry(const double* s_lat, const double* s_lon, int64_t n, const V* vals
     int rc = run_knn(job, stream);
     if (rc != CMX_OK) return rc;
     return idw_from_table<V>(job.idx_out, d2_tab, 1, M, k, k, k_min, power, vals, n, n_batch, layout, out, flag,
-                             stream);
+                             stream, po);
 }
 
 template <typename V>
 int apply_entry(const int32_t* idx, const double* dist, int64_t M, int k_table, const V* vals, int64_t n,
                 int64_t n_batch, int layout, int k_use, int k_min, double power, V* out, int32_t* flag_scratch,
                 void* stream_) {
+    const PeerOut po = take_peer_out();
     if (!idx || !dist || !vals || !out) return CMX_ERR_BAD_ARG;
     if (M < 0 || n_batch < 1 || k_use < 1 || k_use > k_table || k_min < 1) return CMX_ERR_BAD_ARG;
     if (k_use > CMX_MAX_K) return CMX_ERR_K_TOO_LARGE;
@@ -570,7 +589,7 @@ int apply_entry(const int32_t* idx, const double* dist, int64_t M, int k_table, 
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     // without scratch the batched kernel tests every value for finiteness itself
     return idw_from_table<V>(idx, dist, 0, M, k_table, k_use, k_min, power, vals, n, n_batch, layout, out,
-                             flag_scratch, stream);
+                             flag_scratch, stream, po);
 }
 
 }  // namespace

@@ -228,12 +228,16 @@ def _values_layout(values: torch.Tensor, n: int, layout: str | None):
 
 def idw(s_lat, s_lon, values, targets: Targets, *, k: int = 5, power: float = 2.0, k_min: int = 2,
         dtype: torch.dtype = torch.float64, layout: str | None = None, return_neighbours: bool = False,
-        out: torch.Tensor | None = None):
+        out: torch.Tensor | None = None, peer_out: tuple | None = None):
     """Inverse-distance weighting on the device (reference idw.py:155-180).
 
     ``values``: (N,) one slice, or a time/level batch as (T, N) ("batch_major") or
     (N, T) ("sample_major", the fast layout).  Returns (M,) or (T, M) in ``dtype``;
     with ``return_neighbours`` also ``(dist, idx)``.
+
+    ``peer_out = (pointers, m_total, m_offset)`` (batches only): the kernel stores its rows directly into the
+    ``[T][m_total]`` output buffers of several devices at column ``m_offset`` (fused gather over NVLink peer
+    memory, see ``sharding.PeerGather``); nothing is returned in that case.
     """
     lib = _lib.load()
     _apply_search(lib)
@@ -267,7 +271,14 @@ def idw(s_lat, s_lon, values, targets: Targets, *, k: int = 5, power: float = 2.
     k, k_min = int(k), int(k_min)
     m = targets.count
     with torch.cuda.device(dev):
-        if out is None:
+        if peer_out is not None:
+            ptrs, m_total, m_off = peer_out
+            if n_batch < 2 or return_neighbours:
+                raise ValueError("peer_out needs a batch of at least two slices and no neighbour output")
+            arr = (ctypes.c_void_p * len(ptrs))(*[int(q) for q in ptrs])
+            _lib.check(lib.cmx_set_output_peers(arr, len(ptrs), int(m_total), int(m_off)), "cmx_set_output_peers")
+            out = torch.empty(1, dtype=dtype, device=dev)  # placeholder: the call's own output argument is unused
+        elif out is None:
             out = torch.empty((n_batch, m) if n_batch > 1 or values.dim() == 2 else (m,), dtype=dtype, device=dev)
         elif out.dtype != dtype or out.numel() != n_batch * m or not out.is_contiguous():
             raise ValueError("out has the wrong dtype, size or is not contiguous")
@@ -282,6 +293,8 @@ def idw(s_lat, s_lon, values, targets: Targets, *, k: int = 5, power: float = 2.
                 targets.lat.numel(), _ptr(targets.lon), targets.lon.numel(), int(targets.grid), k, k_min,
                 float(power), _ptr(out), _ptr(idx), _ptr(dist), _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "cmx_idw")
+    if peer_out is not None:
+        return None
     if return_neighbours:
         return out, dist, idx
     return out

@@ -111,6 +111,47 @@ def assemble_bands(gathered, bands, n_batch: int, n_cols: int):
     return torch.cat(pieces, dim=1)
 
 
+class PeerGather:
+    """Output buffers for the fused weighting + gather: one ``[T][M]`` array per rank in symmetric (peer-mapped)
+    memory, so that the batched IDW kernel of every rank stores its band into ALL ranks' arrays through NVLink
+    (``cmx_set_output_peers``) and no all-gather / re-assembly pass follows the kernel.
+
+    ``begin()`` makes sure every rank has finished reading the previous result, ``peer_out(r0)`` is what
+    ``kernels.idw(..., peer_out=...)`` needs, ``finish()`` waits until every rank's stores have landed and
+    returns this rank's (complete) array.  Buffers are cached per shape: the rendezvous is a collective.
+    """
+
+    _cache: dict = {}
+
+    def __init__(self, n_batch: int, n_rows: int, n_cols: int, dtype, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.n_cols = n_cols
+        self.m_total = n_rows * n_cols
+        self.buf = symm.empty((n_batch, self.m_total), dtype=dtype, device=device)
+        self.handle = symm.rendezvous(self.buf, self.group)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+
+    @classmethod
+    def get(cls, n_batch, n_rows, n_cols, dtype, device, group=None):
+        key = (n_batch, n_rows, n_cols, dtype, str(device), id(group))
+        if key not in cls._cache:
+            cls._cache[key] = cls(n_batch, n_rows, n_cols, dtype, device, group)
+        return cls._cache[key]
+
+    def begin(self) -> None:
+        self.handle.barrier(channel=0, timeout_ms=60000)
+
+    def peer_out(self, r0: int) -> tuple:
+        return self.ptrs, self.m_total, r0 * self.n_cols
+
+    def finish(self):
+        self.handle.barrier(channel=1, timeout_ms=60000)
+        return self.buf
+
+
 def distributed_bands(compute: Callable, n_rows: int, n_cols: int, n_batch: int, *, dtype, device, group=None,
                       gather: str = "all"):
     """Run ``compute(r0, r1) -> tensor [n_batch, (r1-r0)*n_cols]`` on this rank's band and gather.
@@ -144,7 +185,9 @@ def distributed_idw(s_lat, s_lon, values, t_lat, t_lon, grid: bool, *, k: int, p
     """IDW over all ranks of ``group``: samples replicated, target rows sharded, slabs gathered.
 
     Inputs are device tensors (or NumPy, copied once per rank).  Returns [T, M] (or [M]
-    for a single slice) on this rank's device.
+    for a single slice) on this rank's device.  ``gather``: "all" (NCCL all-gather of padded slabs + re-assembly),
+    "none" (keep the field sharded) or "peer" (batches on a dense grid: the weighting kernel itself stores every
+    band into all ranks' symmetric-memory buffers, no collective after it; device-resident ``values`` only).
     """
     import torch
 
@@ -166,5 +209,21 @@ def distributed_idw(s_lat, s_lon, values, t_lat, t_lon, grid: bool, *, k: int, p
             targets = kernels.Targets.make(lat_band, lon_band, grid, dev)
             return kernels.idw(s_lat, s_lon, values, targets, k=k, power=power, k_min=k_min, dtype=dtype, layout=layout)
 
+    if gather == "peer":
+        # fused weighting + gather: every rank's kernel stores its band into all ranks' buffers (NVLink peer memory)
+        import torch.distributed as dist
+
+        if single or not grid or not (dist.is_initialized() and dist.get_world_size(group) > 1):
+            gather = "all"  # nothing to fuse for one slice / one rank: plain path
+        else:
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+            r0, r1 = row_shards(n_rows, world)[rank]
+            pg = PeerGather.get(n_batch, n_rows, n_cols, dtype, dev, group)
+            pg.begin()
+            if r1 > r0:
+                targets = kernels.Targets.make(t_lat[r0:r1], t_lon, True, dev)
+                kernels.idw(s_lat, s_lon, values, targets, k=k, power=power, k_min=k_min, dtype=dtype, layout=layout,
+                            peer_out=pg.peer_out(r0))
+            return pg.finish()  # NOTE: this rank's cached symmetric buffer; clone() to keep it across calls
     out = distributed_bands(compute, n_rows, n_cols, n_batch, dtype=dtype, device=dev, group=group, gather=gather)
     return out[0] if single else out

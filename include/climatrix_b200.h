@@ -226,6 +226,22 @@ size_t cmx_ok_workspace_bytes(int k, int64_t n_targets);
 int cmx_set_search(int algorithm);
 int cmx_get_search(void);
 
+/* ---- multi-GPU: fused weighting + gather over peer memory ----
+ *
+ * With one process per GPU every rank reconstructs a band of target rows and all ranks need the whole field
+ * (reference: one cm.reconstruct call returns the full grid).  Instead of a separate all-gather after the kernel,
+ * the batched weighting kernels can store each finished row segment directly into the output buffers of ALL ranks
+ * (NVLink peer stores through NVSwitch): call cmx_set_output_peers with the n_peers device pointers of the
+ * [n_batch][m_total] output arrays (peer-mapped, e.g. torch symmetric memory), the total number of targets m_total
+ * and this rank's first target m_offset.  The setting applies to the NEXT cmx_idw_f64/_f32 or cmx_idw_apply_*
+ * call of this thread with n_batch > 1 and is cleared by it; that call's own `out` argument is then unused (but
+ * must be non-null).  n_peers = 0 clears.  Synchronising the ranks before the buffers are read is the caller's
+ * job (e.g. a symmetric-memory barrier).  Errors: CMX_ERR_BAD_ARG; a redirected call with n_batch == 1 returns
+ * CMX_ERR_UNSUPPORTED.
+ */
+#define CMX_MAX_PEERS 8
+int cmx_set_output_peers(void* const* peer_out, int n_peers, int64_t m_total, int64_t m_offset);
+
 /* ---- instrumentation ---- */
 
 /* Kernels launched by this library on the calling thread since the last reset. */

@@ -95,3 +95,19 @@ def test_search_selection_is_host_state():
 
     with pytest.raises(ValueError):
         cm.set_search("kd-tree")
+
+
+def test_output_peers_argument_checks():
+    import ctypes
+
+    lib = _lib.load()
+    one = ctypes.c_void_p(8)
+    arr = (ctypes.c_void_p * 2)(one, one)
+    assert lib.cmx_set_output_peers(None, 0, 0, 0) == 0  # clears
+    assert lib.cmx_set_output_peers(None, 2, 10, 0) == _lib.ERR_BAD_ARG
+    assert lib.cmx_set_output_peers(arr, 9, 10, 0) == _lib.ERR_BAD_ARG
+    assert lib.cmx_set_output_peers(arr, 2, 10, 11) == _lib.ERR_BAD_ARG
+    bad = (ctypes.c_void_p * 2)(one, None)
+    assert lib.cmx_set_output_peers(bad, 2, 10, 0) == _lib.ERR_BAD_ARG
+    assert lib.cmx_set_output_peers(arr, 2, 10, 5) == 0
+    assert lib.cmx_set_output_peers(None, 0, 0, 0) == 0
