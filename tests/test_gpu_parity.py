@@ -511,3 +511,30 @@ def test_launch_counter_counts_kernels():
     la, lo, v, _ = _samples(500, 2)
     K.idw(la, lo, v, K.Targets.make(np.linspace(-80, 80, 9), np.linspace(-170, 170, 9), True, DEV), k=4)
     assert K.launch_count() >= 1
+
+
+# ------------------------------------------------------------------------------------------
+# fused gather: the batched kernels store a band into several [T][m_total] buffers (cmx_set_output_peers)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_batch,k", [(3, 8), (40, 32), (150, 32), (130, 40)])
+def test_idw_batch_peer_output_redirection(n_batch, k):
+    """Two 'peer' buffers on the same device stand in for two ranks: both must receive the band at the
+    requested column offset, bit-identical to the plain output (per-target and neighbour-sharing kernels)."""
+    la, lo, _, rng = _samples(4000, 5 + n_batch)
+    vals = rng.normal(size=(4000, n_batch))
+    tl, to = np.linspace(-60, 60, 33), np.linspace(-170, 170, 70)
+    tg = K.Targets.make(tl, to, True, DEV)
+    plain = K.idw(la, lo, vals, tg, k=k, layout="sample_major")
+    m = tg.count
+    m_total, off = m + 1000, 700
+    bufs = [torch.full((n_batch, m_total), -7.0, dtype=torch.float64, device=DEV) for _ in range(2)]
+    assert K.idw(la, lo, vals, tg, k=k, layout="sample_major",
+                 peer_out=([b.data_ptr() for b in bufs], m_total, off)) is None
+    torch.cuda.synchronize()
+    for b in bufs:
+        assert torch.equal(b[:, off:off + m], plain)
+        assert bool((b[:, :off] == -7.0).all()) and bool((b[:, off + m:] == -7.0).all())
+    # the redirection is consumed by one call: the next plain call is unaffected
+    assert torch.equal(K.idw(la, lo, vals, tg, k=k, layout="sample_major"), plain)
+    with pytest.raises(ValueError):
+        K.idw(la, lo, vals[:, 0], tg, k=k, peer_out=([bufs[0].data_ptr()], m_total, off))
