@@ -136,6 +136,15 @@ int cmx_set_output_peers(void* const* peer_out, int n_peers, int64_t m_total, in
     return CMX_OK;
 }
 
+int cmx_copy_rows_to_host(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
+                          size_t rows, void* stream) {
+    if (!dst || !src || width_bytes > dst_pitch || width_bytes > src_pitch) return CMX_ERR_BAD_ARG;
+    if (rows == 0 || width_bytes == 0) return CMX_OK;
+    CMX_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, cudaMemcpyDeviceToHost,
+                               static_cast<cudaStream_t>(stream)));
+    return CMX_OK;
+}
+
 int64_t cmx_launch_count(void) { return cmx::g_launches; }
 void cmx_reset_launch_count(void) { cmx::g_launches = 0; }
 

@@ -255,9 +255,11 @@ def idw(s_lat, s_lon, values, targets: Targets, *, k: int = 5, power: float = 2.
         with torch.cuda.device(dev):
             main = torch.cuda.current_stream(dev)
             side = torch.cuda.Stream(dev)
+            # search first: the launch is asynchronous, whereas a copy from pageable host memory keeps the host
+            # busy staging - so the upload below really runs while the search kernel computes
+            dist, idx = knn(s_lat, s_lon, targets, k)
             with torch.cuda.stream(side):
                 vals_d = values.to(device=dev, dtype=dtype, non_blocking=True)
-            dist, idx = knn(s_lat, s_lon, targets, k)
             main.wait_stream(side)
             vals_d.record_stream(main)
             res = idw_apply(idx, dist, vals_d, k=k, power=power, k_min=k_min, dtype=dtype, layout=layout, n_samples=n)

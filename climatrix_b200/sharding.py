@@ -47,6 +47,10 @@ def idw_on_devices(s_lat, s_lon, values, t_lat, t_lon, grid: bool, *, k: int, po
 
     if devices is None or len(devices) <= 1:
         dev = kernels._require_cuda(devices[0] if devices else device)
+        piped = _idw_two_bands(s_lat, s_lon, values, t_lat, t_lon, grid, k=k, power=power, k_min=k_min, dtype=dtype,
+                               dev=dev, layout=layout) if not return_neighbours else None
+        if piped is not None:
+            return piped
         with torch.cuda.device(dev):
             targets = kernels.Targets.make(t_lat, t_lon, grid, dev)
             res = kernels.idw(s_lat, s_lon, values, targets, k=k, power=power, k_min=k_min, dtype=dtype,
@@ -72,6 +76,68 @@ def idw_on_devices(s_lat, s_lon, values, t_lat, t_lon, grid: bool, *, k: int, po
             pending.append(out)
     parts = [_to_host(o) for o in pending]
     return np.concatenate(parts, axis=-1)
+
+
+def _idw_two_bands(s_lat, s_lon, values, t_lat, t_lon, grid, *, k, power, k_min, dtype, dev, layout,
+                   min_bytes: int = 1 << 28):
+    """Large host-resident batch on a dense grid, one device: hide the device->host copy of the result.
+
+    The result of a big reconstruction (C5: 1.9 GB) takes tens of milliseconds to cross PCIe, and none of it can
+    start before the neighbour search has finished.  So the target rows are cut into a large first band and a
+    small second one: the first band's result streams into its columns of the page-locked output (one strided
+    DMA, ``cmx_copy_rows_to_host``) while the second band is still searching.  The upload of the values is
+    issued after the first search launch, so it overlaps too.  Returns None when the case does not apply.
+    """
+    import torch
+
+    from . import _lib, kernels
+
+    if not grid or not isinstance(values, np.ndarray) or values.ndim != 2:
+        return None
+    n_rows, n_cols = len(t_lat), len(t_lon)
+    n = len(s_lat)
+    if layout not in ("sample_major", "batch_major"):
+        return None
+    n_batch = values.shape[1] if layout == "sample_major" else values.shape[0]
+    esize = 8 if dtype == torch.float64 else 4
+    m_total = n_rows * n_cols
+    if n_batch < 2 or n_rows < 256 or m_total * n_batch * esize < min_bytes:
+        return None
+    split = (int(0.88 * n_rows) // 16) * 16
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        main = torch.cuda.current_stream(dev)
+        up, down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        try:
+            host = torch.empty((n_batch, m_total), dtype=dtype, pin_memory=True)
+        except RuntimeError:
+            return None
+        s_lat_d, s_lon_d = kernels._as_f64(s_lat, dev), kernels._as_f64(s_lon, dev)
+        t_lat_d, t_lon_d = kernels._as_f64(t_lat, dev), kernels._as_f64(t_lon, dev)
+        keep, vals_d, col = [], None, 0
+        for r0, r1 in ((0, split), (split, n_rows)):
+            tg = kernels.Targets(t_lat_d[r0:r1].contiguous(), t_lon_d, True)
+            dist, idx = kernels.knn(s_lat_d, s_lon_d, tg, k)  # asynchronous launch
+            if vals_d is None:  # pageable upload: the host stages it while the search kernel runs
+                with torch.cuda.stream(up):
+                    vals_d = torch.as_tensor(values).to(device=dev, dtype=dtype, non_blocking=True)
+                main.wait_stream(up)
+                vals_d.record_stream(main)
+            band = kernels.idw_apply(idx, dist, vals_d, k=k, power=power, k_min=k_min, dtype=dtype, layout=layout,
+                                     n_samples=n)
+            m_band = (r1 - r0) * n_cols
+            stream = down if r1 < n_rows else main  # the last band has nothing left to overlap with
+            if stream is down:
+                down.wait_stream(main)
+                band.record_stream(down)
+            _lib.check(lib.cmx_copy_rows_to_host(host.data_ptr() + col * esize, m_total * esize, band.data_ptr(),
+                                                 m_band * esize, m_band * esize, n_batch, stream.cuda_stream),
+                       "cmx_copy_rows_to_host")
+            keep.append((band, dist, idx))
+            col += m_band
+        down.synchronize()
+        main.synchronize()
+    return host.numpy()
 
 
 def _to_host(t):

@@ -242,6 +242,14 @@ int cmx_get_search(void);
 #define CMX_MAX_PEERS 8
 int cmx_set_output_peers(void* const* peer_out, int n_peers, int64_t m_total, int64_t m_offset);
 
+/* ---- host transfer helper ----
+ * Asynchronous strided device -> host copy (cudaMemcpy2DAsync): `rows` rows of `width_bytes` bytes from a device
+ * array with row pitch src_pitch into a (page-locked) host array with row pitch dst_pitch.  Lets a band of target
+ * rows [T][M_band] land in its columns of the caller's [T][M] result while the next band is still computing.
+ */
+int cmx_copy_rows_to_host(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
+                          size_t rows, void* stream);
+
 /* ---- instrumentation ---- */
 
 /* Kernels launched by this library on the calling thread since the last reset. */

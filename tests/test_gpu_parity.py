@@ -538,3 +538,23 @@ def test_idw_batch_peer_output_redirection(n_batch, k):
     assert torch.equal(K.idw(la, lo, vals, tg, k=k, layout="sample_major"), plain)
     with pytest.raises(ValueError):
         K.idw(la, lo, vals[:, 0], tg, k=k, peer_out=([bufs[0].data_ptr()], m_total, off))
+
+
+@pytest.mark.parametrize("layout", ["sample_major", "batch_major"])
+def test_idw_two_band_pipeline_equals_single_call(layout):
+    """Host path for large batches: two row bands, the first one's device->host copy overlapped with the
+    second one's search (sharding._idw_two_bands).  Same bits as one call over the whole grid."""
+    from climatrix_b200.sharding import _idw_two_bands
+
+    la, lo, _, rng = _samples(3000, 77)
+    vals = rng.normal(size=(3000, 5))
+    host_vals = vals if layout == "sample_major" else np.ascontiguousarray(vals.T)
+    tl, to = np.linspace(-80, 80, 300), np.linspace(-170, 170, 41)
+    got = _idw_two_bands(la, lo, host_vals, tl, to, True, k=12, power=2.0, k_min=2, dtype=torch.float64,
+                         dev=torch.device(DEV), layout=layout, min_bytes=0)
+    assert got is not None and got.shape == (5, 300 * 41)
+    ref = K.idw(la, lo, vals, K.Targets.make(tl, to, True, DEV), k=12, layout="sample_major").cpu().numpy()
+    np.testing.assert_array_equal(got, ref)
+    # too small / not a batch: the pipeline declines and the plain path runs
+    assert _idw_two_bands(la, lo, host_vals, tl, to, True, k=12, power=2.0, k_min=2, dtype=torch.float64,
+                          dev=torch.device(DEV), layout=layout) is None
