@@ -133,7 +133,8 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
                  backend: Literal["vectorized", "loop"] | None = None, nlags: int | None = None,
                  anisotropy_scaling: float | None = None, coordinates_type: str | None = None,
                  variogram_model: str | None = None, pseudo_inv: bool = False, *,
-                 n_closest_points: int | None = None, k: int | None = None, dtype="float64", device=None):
+                 n_closest_points: int | None = None, k: int | None = None, dtype="float64", device=None,
+                 return_variance: bool = False):
         super().__init__(dataset, target_domain)
         extra = extra_dimensions(dataset.domain)
         if extra:
@@ -165,6 +166,10 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
         if self.dtype not in ("float64", "float32"):
             raise TypeError("dtype must be float64 or float32")
         self.device = device
+        # pykrige's execute() also returns the kriging variance, which climatrix drops (kriging.py:236); with
+        # return_variance=True the moving-window paths keep it in ``self.variance_`` (target shape, data units^2)
+        self.return_variance = bool(return_variance)
+        self.variance_ = None
         self.variogram_model_parameters = None
         self.lags = None
         self.semivariance = None
@@ -247,10 +252,13 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
                     gxm, gym = np.meshgrid(xpts, ypts)
                     gx, gy = gxm.ravel(), gym.ravel()
                 d2, idx = kernels.knn3(unit(x_adj, y_adj), unit(gx, gy), self.n_closest_points)
-                out, nsing = kernels.ok_solve(
+                res = kernels.ok_solve(
                     xs, ys, zs.to(tdtype), idx, d2, variogram_model=self.variogram_model, params=params,
                     geographic=True, exact_values=True, out_scale=float(v_std), out_shift=float(v_mean), dtype=tdtype,
+                    return_sigmasq=self.return_variance,
                 )
+                out, nsing = res[0], res[-1]
+                sig = res[1] if self.return_variance else None
                 n_sing = int(nsing.item())
                 if n_sing:
                     raise np.linalg.LinAlgError(f"{n_sing} kriging windows are singular")
@@ -262,11 +270,14 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
                 else:
                     tx, _ = _anisotropy(xpts, np.full_like(xpts, yc), xc, yc, scaling)
                     _, ty = _anisotropy(np.full_like(ypts, xc), ypts, xc, yc, scaling)
-                out, nsing = kernels.ok_moving_window(
+                res = kernels.ok_moving_window(
                     xs, ys, zs.to(tdtype), tx, ty, not sparse_target, k=self.n_closest_points,
                     variogram_model=self.variogram_model, params=params, exact_values=True,
                     out_scale=float(v_std), out_shift=float(v_mean), dtype=tdtype,
+                    return_sigmasq=self.return_variance,
                 )
+                out, nsing = res[0], res[-1]
+                sig = res[1] if self.return_variance else None
                 n_sing = int(nsing.item())
                 if n_sing:
                     # pykrige raises LinAlgError from scipy.linalg.solve on a singular window
@@ -275,8 +286,13 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
                     )
                 values = out.cpu().numpy()
             else:
+                sig = None
                 values = self._global(torch, dev, xs, ys, zs, xpts, ypts, sparse_target, xc, yc, scaling, params,
                                       geographic, v_mean, v_std, tdtype)
+            if self.return_variance and sig is not None:
+                # sigma^2 comes out in standardised units (values were z-scored): back to data units^2
+                shape = (ypts.size, xpts.size) if not sparse_target else (xpts.size,)
+                self.variance_ = (sig.double().cpu().numpy() * float(v_std) ** 2).reshape(shape)
 
         log.debug("Reconstruction completed.")
         values = np.asarray(values, dtype=np.float64 if self.dtype == "float64" else np.float32)

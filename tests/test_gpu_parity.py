@@ -558,3 +558,51 @@ def test_idw_two_band_pipeline_equals_single_call(layout):
     # too small / not a batch: the pipeline declines and the plain path runs
     assert _idw_two_bands(la, lo, host_vals, tl, to, True, k=12, power=2.0, k_min=2, dtype=torch.float64,
                           dev=torch.device(DEV), layout=layout) is None
+
+
+def test_ok_reconstructor_surfaces_the_kriging_variance():
+    """pykrige's execute() returns (z, sigma^2); climatrix drops sigma^2 (kriging.py:236).  With
+    return_variance=True the reconstructor keeps it, in data units^2."""
+    from oracle.ok_oracle import normalize_axis, ok_oracle, standardize_values
+
+    la, lo, v, _ = _samples(700, 21)
+    tl, to = np.linspace(-80, 80, 13), np.linspace(-170, 170, 17)
+    rec = cm.OrdinaryKrigingReconstructor(static_sparse(la, lo, v), cm.Domain.from_lat_lon(tl, to), n_closest_points=12,
+                                          variogram_model="spherical", anisotropy_scaling=1.0, return_variance=True)
+    got = rec.reconstruct().da.values
+    ref, model = ok_oracle(la, lo, v, tl, to, False, n_closest_points=12, variogram_model="spherical",
+                           anisotropy_scaling=1.0, return_model=True)
+    assert np.max(np.abs(got - ref)) <= OK_RTOL * np.max(np.abs(ref))
+    _, ss = model.execute("grid", normalize_axis(to)[-1], normalize_axis(tl)[-1], backend="loop", n_closest_points=12)
+    v_std = standardize_values(np.asarray(v, float))[1]
+    want = np.ma.getdata(ss) * v_std ** 2
+    assert rec.variance_.shape == (13, 17)
+    assert np.max(np.abs(rec.variance_ - want)) <= OK_RTOL * np.max(np.abs(want))
+
+
+def test_sparse_matching_like_comparison():
+    """comparison.py:112-165: nearest true point per predicted point, optional exclusive distance bound."""
+    from scipy.spatial import cKDTree
+
+    from climatrix_b200.matching import match_nearest, sparse_difference
+
+    rng = np.random.default_rng(9)
+    true_pts = np.stack((rng.uniform(-90, 90, 3000), rng.uniform(-180, 180, 3000)), 1)
+    pred_pts = np.concatenate((true_pts[:500] + rng.normal(scale=1e-3, size=(500, 2)), true_pts[500:520],
+                               np.stack((rng.uniform(-90, 90, 300), rng.uniform(-180, 180, 300)), 1)))
+    tv, pv = rng.normal(size=3000), rng.normal(size=len(pred_pts))
+    tree = cKDTree(true_pts)
+    for thr in (None, 0.0, 0.01, 5.0):
+        idx, valid, dist = match_nearest(pred_pts, true_pts, thr)
+        if thr is None:
+            d0, i0 = tree.query(pred_pts)
+            ok0 = np.ones(len(d0), bool)
+        else:
+            d0, i0 = tree.query(pred_pts, distance_upper_bound=np.finfo(float).eps if thr == 0.0 else thr)
+            ok0 = d0 < np.inf
+        np.testing.assert_array_equal(valid, ok0)
+        np.testing.assert_array_equal(idx[valid], i0[ok0])
+        np.testing.assert_array_equal(dist[valid], d0[ok0])
+        diff, kept = sparse_difference(pv, pred_pts, tv, true_pts, thr)
+        np.testing.assert_array_equal(kept, np.where(ok0)[0])
+        np.testing.assert_array_equal(diff, (pv - tv[np.where(ok0, i0, 0)])[ok0])
