@@ -103,7 +103,7 @@ def _idw_two_bands(s_lat, s_lon, values, t_lat, t_lon, grid, *, k, power, k_min,
     m_total = n_rows * n_cols
     if n_batch < 2 or n_rows < 256 or m_total * n_batch * esize < min_bytes:
         return None
-    split = (int(0.88 * n_rows) // 16) * 16
+    split = (int(0.92 * n_rows) // 16) * 16  # small second band: its search must still cover the first band's download
     lib = _lib.load()
     with torch.cuda.device(dev):
         main = torch.cuda.current_stream(dev)
