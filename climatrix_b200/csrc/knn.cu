@@ -24,6 +24,7 @@
 //   * the final re-rank leaves the k neighbours in registers, where the IDW
 //     weights and the weighted mean are evaluated before anything is stored.
 #include <limits.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "rerank.cuh"
@@ -993,8 +994,9 @@ struct Plan {
 
 // Targets per thread: 16 for large sample sets (fewest shared-memory loads per pair; throughput bound),
 // 8 by default, 2 or 1 for small problems (latency bound: per-target re-ranks are serial inside a warp,
-// so they are spread over more warps).  When even that leaves warps idle (a multi-GPU band of a big
-// job), the sample range is split into nseg segments so that there are >= ~3 work units per warp.
+// so they are spread over more warps).  A band of a big job (multi-GPU rank, second band of the host
+// pipeline) has too few tiles for that: there the sample range is split into nseg segments and tile
+// height and nseg come from a small cost model.
 Plan make_plan(long long n, long long n_a, long long n_b, int grid) {
     const long long M = grid ? n_a * n_b : n_a;
     const int sms = sm_count();
@@ -1011,10 +1013,34 @@ Plan make_plan(long long n, long long n_a, long long n_b, int grid) {
     const long long warps16 = (long long)sms * ctas_per_sm(16) * WARPS, warps8 = (long long)sms * ctas_per_sm(8) * WARPS;
     Plan p;
     p.nseg = 1;
-    if (n >= 262144 && t16 >= warps16 / 2) {
+    const long long n_st = (n + SS - 1) / SS;
+    if (n >= 262144 && t16 >= 2 * warps16) {
+        // plenty of tiles: biggest tile, no split (a little splitting only if it evens out the last round)
         p.qpt = 16, p.tiles = t16, p.tiles_c = tc16;
-        const long long n_st = (n + SS - 1) / SS;
         while (p.nseg < 8 && p.tiles * p.nseg < 3 * warps16 && n_st / (p.nseg * 2) >= 128) p.nseg *= 2;
+    } else if (n >= 262144 && t16 * 8 >= warps16) {
+        // A band of a big job (one rank of a multi-GPU run, the second band of the host pipeline): fewer tiles
+        // than a few rounds of warps.  Pick tile height and sample split from a cost model fitted to sweeps on
+        // B200 (DESIGN.md K1 "planner"): padded rows x (1 + re-rank overhead per segment) x the cost of the
+        // partially filled last round of work units (the kernel is pipe-bound, so a round with a fraction f of
+        // the warps busy costs about 0.3 + 0.7 f of a full one).
+        double best = 1e300;
+        for (int qi = 0; qi < 2; ++qi) {
+            const int q = qi ? 8 : 16;
+            const long long tiles = qi ? t8 : t16, warps = qi ? warps8 : warps16;
+            const long long rows = grid ? ((n_a + q - 1) / q) * q : tiles;  // padded work, in rows (or tiles)
+            for (int sg = 1; sg <= 8; sg *= 2) {
+                if (sg > 1 && n_st / (sg * 2) < 128) break;
+                const double u = (double)tiles * sg / (double)warps;
+                const double fl = floor(u), fr = u - fl;
+                const double rounds = fl + (fr > 1e-9 ? 0.3 + 0.7 * fr : 0.0);
+                const double cost = (double)rows * (grid ? 1.0 : q) * (1.0 + 0.01 * (1.0e6 / (double)n) * sg) * rounds / u;
+                if (cost < best) {
+                    best = cost;
+                    p.qpt = q, p.tiles = tiles, p.tiles_c = qi ? tc8 : tc16, p.nseg = sg;
+                }
+            }
+        }
     } else if (t8 >= 2 * warps8) {
         p.qpt = 8, p.tiles = t8, p.tiles_c = tc8;
     } else if (t2 >= warps8) {
@@ -1022,6 +1048,15 @@ Plan make_plan(long long n, long long n_a, long long n_b, int grid) {
     } else {
         p.qpt = 1, p.tiles = t1, p.tiles_c = tc1;
     }
+#ifdef CMX_PLAN_ENV  // tuning builds only: CMX_FORCE_QPT / CMX_FORCE_NSEG override the planner
+    if (const char* fq = getenv("CMX_FORCE_QPT")) {
+        const int q = atoi(fq);
+        if (q == 16) p.qpt = 16, p.tiles = t16, p.tiles_c = tc16;
+        if (q == 8) p.qpt = 8, p.tiles = t8, p.tiles_c = tc8;
+        p.nseg = 1;
+    }
+    if (const char* fs = getenv("CMX_FORCE_NSEG")) p.nseg = atoi(fs);
+#endif
     return p;
 }
 }  // namespace
