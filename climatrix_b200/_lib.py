@@ -42,6 +42,7 @@ SIGNATURES = {
     "cmx_knn3": (c_int, [_P, _P, _P, c_i64, _P, _P, _P, c_i64, c_int, _P, _P, _P]),
     "cmx_ok_solve_f64": (c_int, [_P, _P, _P, c_i64, _P, _P, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_double), c_int, c_double, c_double, _P, _P, _P, _P]),
     "cmx_ok_solve_f32": (c_int, [_P, _P, _P, c_i64, _P, _P, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_double), c_int, c_double, c_double, _P, _P, _P, _P]),
+    "cmx_knn_plan": (c_int, [c_i64, c_i64, c_i64, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "cmx_set_search": (c_int, [c_int]),
     "cmx_copy_rows_to_host": (c_int, [_P, c_size_t, _P, c_size_t, c_size_t, c_size_t, _P]),
     "cmx_set_output_peers": (c_int, [ctypes.POINTER(ctypes.c_void_p), c_int, c_i64, c_i64]),

@@ -111,6 +111,12 @@ const char* cmx_strerror(int code) {
 
 const char* cmx_last_cuda_error(void) { return cmx::g_cuda_err; }
 
+int cmx_knn_plan(int64_t n_samples, int64_t n_a, int64_t n_b, int grid, int* tile_rows, int* sample_segments) {
+    if (!tile_rows || !sample_segments || n_samples < 0 || n_a < 0 || n_b < 0) return CMX_ERR_BAD_ARG;
+    cmx::knn_plan(n_samples, n_a, n_b, grid, tile_rows, sample_segments);
+    return CMX_OK;
+}
+
 int cmx_set_search(int algorithm) {
     if (algorithm != CMX_SEARCH_BRUTE && algorithm != CMX_SEARCH_BINNED) return CMX_ERR_BAD_ARG;
     const int prev = cmx::g_search;

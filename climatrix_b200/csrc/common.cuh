@@ -66,6 +66,7 @@ size_t knn_workspace_bytes(int k);
 // with room for the partial-list tables of the sample split the planner would choose for these sizes
 size_t knn_workspace_bytes_for(int k, long long n, long long n_a, long long n_b, int grid);
 int run_knn(const KnnJob& job, cudaStream_t stream);
+void knn_plan(long long n, long long n_a, long long n_b, int grid, int* tile_rows, int* sample_segments);
 
 // ---- device helpers -----------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -1077,6 +1077,12 @@ size_t knn_workspace_bytes_for(int k, long long n, long long n_a, long long n_b,
     return base + (size_t)M * p.nseg * 32 * list_slots(k) * (sizeof(double) + sizeof(int)) + 512;
 }
 
+void knn_plan(long long n, long long n_a, long long n_b, int grid, int* tile_rows, int* sample_segments) {
+    const Plan p = make_plan(n, n_a, n_b, grid);
+    *tile_rows = p.qpt;
+    *sample_segments = p.nseg;
+}
+
 int run_knn(const KnnJob& job, cudaStream_t stream) {
     if (!job.s_a || !job.s_b || !job.t_a || !job.t_b) return CMX_ERR_BAD_ARG;
     if (job.n < 0 || job.n_a < 0 || job.n_b < 0 || job.k < 1) return CMX_ERR_BAD_ARG;

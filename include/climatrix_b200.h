@@ -209,6 +209,11 @@ int cmx_ok_solve_f32(const double* s_x, const double* s_y, const float* z, int64
 /* total scratch for cmx_ok_mw_* (includes the kNN scratch) */
 size_t cmx_ok_workspace_bytes(int k, int64_t n_targets);
 
+/* Work decomposition cmx_knn (brute force) would use for these sizes on the current device: targets per thread
+ * (tile height in rows: 16, 8, 2 or 1) and the number of sample segments (1 = no split).  Host-only query, for
+ * benchmarks and tests of the planner (DESIGN.md K1 "Planner").  Returns CMX_OK or CMX_ERR_BAD_ARG. */
+int cmx_knn_plan(int64_t n_samples, int64_t n_a, int64_t n_b, int grid, int* tile_rows, int* sample_segments);
+
 /* ---- neighbour-search algorithm ----
  *
  * Every entry point that searches planar neighbours (cmx_knn, cmx_idw_*, cmx_ok_mw_*) uses the algorithm

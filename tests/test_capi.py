@@ -111,3 +111,24 @@ def test_output_peers_argument_checks():
     assert lib.cmx_set_output_peers(bad, 2, 10, 0) == _lib.ERR_BAD_ARG
     assert lib.cmx_set_output_peers(arr, 2, 10, 5) == 0
     assert lib.cmx_set_output_peers(None, 0, 0, 0) == 0
+
+
+def test_planner_choices_for_bands_of_a_big_job():
+    """make_plan's cost model must keep picking what the B200 sweep measured as best
+    (profiles/r01_planner_sweep.txt); without a device the library plans for 148 SMs."""
+    import ctypes
+
+    lib = _lib.load()
+
+    def plan(n, rows, cols, grid=1):
+        q, s = ctypes.c_int(0), ctypes.c_int(0)
+        assert lib.cmx_knn_plan(n, rows, cols, grid, ctypes.byref(q), ctypes.byref(s)) == 0
+        return q.value, s.value
+
+    assert plan(1_000_000, 1801, 3600) == (16, 1)      # the whole C5 grid: big tiles, no split
+    assert plan(1_000_000, 153, 3600) == (16, 2)       # second band of the host pipeline
+    assert plan(1_000_000, 225, 3600) == (8, 4)        # one rank of an 8-GPU run
+    assert plan(1_000_000, 450, 3600)[1] in (2, 4)     # 4 GPUs: measured tie
+    assert plan(100_000, 721, 1440) == (2, 1)          # C3: re-rank bound, small tiles spread the serial re-ranks
+    assert plan(1_000, 180, 360)[0] in (1, 2)          # C1: latency bound, spread over the SMs
+    assert lib.cmx_knn_plan(10, 1, 1, 1, None, None) == _lib.ERR_BAD_ARG
