@@ -266,6 +266,7 @@ def distributed_idw(s_lat, s_lon, values, t_lat, t_lon, grid: bool, *, k: int, p
     single = not (hasattr(values, "dim") and values.dim() == 2) and not (isinstance(values, np.ndarray) and values.ndim == 2)
     n_batch = 1 if single else (values.shape[1] if layout == "sample_major" else values.shape[0])
 
+    custom_compute = compute is not None
     if compute is None:
         def compute(r0, r1):  # noqa: E306
             if r1 == r0:
@@ -279,8 +280,8 @@ def distributed_idw(s_lat, s_lon, values, t_lat, t_lon, grid: bool, *, k: int, p
         # fused weighting + gather: every rank's kernel stores its band into all ranks' buffers (NVLink peer memory)
         import torch.distributed as dist
 
-        if single or not grid or not (dist.is_initialized() and dist.get_world_size(group) > 1):
-            gather = "all"  # nothing to fuse for one slice / one rank: plain path
+        if custom_compute or single or not grid or not (dist.is_initialized() and dist.get_world_size(group) > 1):
+            gather = "all"  # nothing to fuse for one slice / one rank / a caller-supplied band function: plain path
         else:
             world, rank = dist.get_world_size(group), dist.get_rank(group)
             r0, r1 = row_shards(n_rows, world)[rank]

@@ -62,6 +62,11 @@ def _worker(rank, world, port, n_lat, q):
             return torch.from_numpy(ref)
 
         out = distributed_idw(s_lat, s_lon, vals, t_lat, t_lon, True, k=6, compute=compute, dtype=torch.float64)
+        # the fused peer-store gather needs the CUDA kernels: with a caller-supplied band function it must fall
+        # back to the collective gather and give the same field
+        out_peer = distributed_idw(s_lat, s_lon, vals, t_lat, t_lon, True, k=6, compute=compute, dtype=torch.float64,
+                                   gather="peer")
+        assert torch.equal(out, out_peer)
         ref = idw_oracle_batched(sparse_points(s_lat, s_lon), vals, dense_points(t_lat, t_lon), k=6)
         q.put((rank, bool(np.array_equal(out.numpy(), ref)), tuple(out.shape)))
     finally:
