@@ -2,6 +2,7 @@
 """Benchmark of the IDW / ordinary-kriging reconstruction hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c5|c3|c1|c2|c4]
+                    [--search brute|binned] [--gather peer|nccl] [--no-binned] [--no-e2e] [--no-cpu-baseline]
 
 Headline workload (BASELINE.json configs[4], the largest IDW k=32 configuration; it fits one GPU):
   IDW, 1 000 000 station samples -> 0.1 deg global grid (1801 x 3600) x 37 pressure levels, k=32, power=2.
@@ -10,8 +11,14 @@ the batched weighting), inputs resident in HBM.  metric = target points / second
 SURVEY.md section 8d); ``output_values_per_s`` is M*37 / step time.
 
 Under ``torchrun`` (N > 1, one rank per GPU) the target rows are sharded over the ranks
-(strong scaling: the job is fixed), samples are replicated, and the output slabs are
-all-gathered over NCCL inside the timed step.
+(strong scaling: the job is fixed), samples are replicated, and every rank holds the whole
+field at the end of the timed step.
+
+The headline numbers use the brute-force neighbour search K1 (north_star); the same step with the cell-binned search
+K1c (identical output) is measured right after it and reported as ``binned_search`` in the same JSON line
+(``--search binned`` makes it the headline instead, ``--no-binned`` skips it).  For N > 1 ``config.gather`` says how
+the bands became the full field on every rank: stored by the weighting kernel into all ranks' buffers over NVLink
+peer memory (default) or an NCCL all-gather (``--gather nccl``).
 
 ``--impl reference`` times the reference's CPU implementation of the same path (scipy cKDTree +
 the NumPy epilogue of idw.py:155-180, restated in oracle/ with the real scipy) on the host cores,
