@@ -252,7 +252,7 @@ def main():
     import torch
 
     from climatrix_b200 import kernels as K
-    from climatrix_b200.sharding import distributed_bands, idw_on_devices, row_shards
+    from climatrix_b200.sharding import distributed_bands, row_shards
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: climatrix_b200 has no CPU fallback")

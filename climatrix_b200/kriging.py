@@ -27,7 +27,7 @@ from typing import ClassVar, Literal
 
 import numpy as np
 
-from .dataset import AxisType, BaseClimatrixDataset, Domain
+from .dataset import BaseClimatrixDataset, Domain
 from .exceptions import OperationNotSupportedForDynamicDatasetError
 from .idw import extra_dimensions
 from .plugin import BaseReconstructor, Hyperparameter
