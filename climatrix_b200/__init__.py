@@ -32,8 +32,9 @@ from .kriging import OrdinaryKrigingReconstructor  # noqa: F401
 
 
 def set_search(algorithm: str) -> str:
-    """Neighbour search used by both reconstructors: ``"brute"`` (K1, default) or ``"binned"`` (K1c, cell-binned;
-    same results, ~N/k times fewer distance evaluations).  Returns the previous setting."""
+    """Neighbour search used by both reconstructors: ``"auto"`` (default: the cell-binned search K1c whenever its
+    scratch fits), ``"brute"`` (K1, every pair evaluated - the north_star kernel) or ``"binned"`` (K1c; same results,
+    ~N/k times fewer distance evaluations).  Returns the previous setting."""
     from . import kernels
 
     return kernels.set_search(algorithm)
@@ -64,10 +65,25 @@ def install_into_climatrix() -> bool:
     ref_base.BaseReconstructor._registry["ok"] = OrdinaryKrigingReconstructor
     members = {name.upper(): cls for name, cls in ref_base.BaseReconstructor._registry.items()}
     new_enum = enum.Enum("ReconstructionType", members)
+    # type.py:14-76 defines get / list / __missing__ as MODULE-LEVEL functions and attaches them as
+    # classmethods; re-attach the same functions so that they bind to the rebuilt enum (copying the bound
+    # methods of the old enum would keep resolving "idw" to the CPU class)
+    old_enum = ref_type.ReconstructionType
     for attr in ("get", "list", "__missing__"):
-        if hasattr(ref_type.ReconstructionType, attr):
-            setattr(new_enum, attr, getattr(ref_type.ReconstructionType, attr))
+        fn = getattr(ref_type, attr, None)
+        if not callable(fn) or isinstance(fn, type):
+            bound = getattr(old_enum, attr, None)
+            fn = getattr(bound, "__func__", None)
+        if fn is not None:
+            setattr(new_enum, attr, classmethod(fn))
     ref_type.ReconstructionType = new_enum
+    # modules that did `from climatrix.reconstruct.type import ReconstructionType` at import time hold the old enum
+    import sys
+
+    for mod in list(sys.modules.values()):
+        name = getattr(mod, "__name__", "") or ""
+        if name.startswith("climatrix") and getattr(mod, "ReconstructionType", None) is old_enum:
+            setattr(mod, "ReconstructionType", new_enum)
     return True
 
 

@@ -16,6 +16,19 @@ _HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 
 c_void_p, c_int, c_i64, c_double, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_size_t
 
+MAX_PEERS = 8
+
+
+class Options(ctypes.Structure):
+    """``cmx_options`` of include/climatrix_b200.h: everything optional about a call, passed explicitly."""
+
+    _fields_ = [("search", c_int), ("n_peers", c_int), ("peer_out", c_void_p * MAX_PEERS), ("m_total", c_i64),
+                ("m_offset", c_i64)]
+
+
+SEARCH_AUTO, SEARCH_BRUTE, SEARCH_BINNED = 0, 1, 2
+_OPT = ctypes.POINTER(Options)
+
 # name -> (restype, argtypes)   [pointers are passed as integers / c_void_p]
 _P = c_void_p
 SIGNATURES = {
@@ -24,29 +37,27 @@ SIGNATURES = {
     "cmx_last_cuda_error": (ctypes.c_char_p, []),
     "cmx_knn_workspace_bytes": (c_size_t, [c_int]),
     "cmx_knn_workspace_bytes_for": (c_size_t, [c_int, c_i64, c_i64, c_i64, c_int]),
-    "cmx_knn": (c_int, [_P, _P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "cmx_knn": (c_int, [_P, _P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, _P, _P, _P, c_size_t, _OPT, _P]),
     "cmx_idw_workspace_bytes": (c_size_t, [c_int, c_i64, c_i64]),
-    "cmx_idw_f64": (c_int, [_P, _P, c_i64, _P, c_i64, c_int, _P, c_i64, _P, c_i64, c_int, c_int, c_int, c_double, _P, _P, _P, _P, c_size_t, _P]),
-    "cmx_idw_f32": (c_int, [_P, _P, c_i64, _P, c_i64, c_int, _P, c_i64, _P, c_i64, c_int, c_int, c_int, c_double, _P, _P, _P, _P, c_size_t, _P]),
-    "cmx_idw_apply_f64": (c_int, [_P, _P, c_i64, c_int, _P, c_i64, c_i64, c_int, c_int, c_int, c_double, _P, _P, _P]),
-    "cmx_idw_apply_f32": (c_int, [_P, _P, c_i64, c_int, _P, c_i64, c_i64, c_int, c_int, c_int, c_double, _P, _P, _P]),
+    "cmx_idw_f64": (c_int, [_P, _P, c_i64, _P, c_i64, c_int, _P, c_i64, _P, c_i64, c_int, c_int, c_int, c_double, _P, _P, _P, _P, c_size_t, _OPT, _P]),
+    "cmx_idw_f32": (c_int, [_P, _P, c_i64, _P, c_i64, c_int, _P, c_i64, _P, c_i64, c_int, c_int, c_int, c_double, _P, _P, _P, _P, c_size_t, _OPT, _P]),
+    "cmx_idw_apply_f64": (c_int, [_P, _P, c_i64, c_int, _P, c_i64, c_i64, c_int, c_int, c_int, c_double, _P, _P, _OPT, _P]),
+    "cmx_idw_apply_f32": (c_int, [_P, _P, c_i64, c_int, _P, c_i64, c_i64, c_int, c_int, c_int, c_double, _P, _P, _OPT, _P]),
     "cmx_variogram_minmax": (c_int, [_P, _P, c_i64, c_int, _P, _P]),
     "cmx_variogram_bins": (c_int, [_P, _P, _P, c_i64, c_int, c_int, _P, _P, _P, _P, _P]),
     "cmx_ok_workspace_bytes": (c_size_t, [c_int, c_i64]),
-    "cmx_ok_mw_f64": (c_int, [_P, _P, _P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, c_int, c_int, ctypes.POINTER(c_double), c_int, c_double, c_double, _P, _P, _P, _P, c_size_t, _P]),
-    "cmx_ok_mw_f32": (c_int, [_P, _P, _P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, c_int, c_int, ctypes.POINTER(c_double), c_int, c_double, c_double, _P, _P, _P, _P, c_size_t, _P]),
+    "cmx_ok_mw_f64": (c_int, [_P, _P, _P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, c_int, c_int, ctypes.POINTER(c_double), c_int, c_double, c_double, _P, _P, _P, _P, c_size_t, _OPT, _P]),
+    "cmx_ok_mw_f32": (c_int, [_P, _P, _P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, c_int, c_int, ctypes.POINTER(c_double), c_int, c_double, c_double, _P, _P, _P, _P, c_size_t, _OPT, _P]),
     "cmx_timing_enable": (None, [c_int]),
     "cmx_timing_reset": (None, []),
     "cmx_timing_read": (c_int, [c_int, ctypes.POINTER(c_double), ctypes.POINTER(c_i64)]),
     "cmx_fp32_peak_tflops": (c_double, []),
     "cmx_knn3": (c_int, [_P, _P, _P, c_i64, _P, _P, _P, c_i64, c_int, _P, _P, _P]),
-    "cmx_ok_solve_f64": (c_int, [_P, _P, _P, c_i64, _P, _P, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_double), c_int, c_double, c_double, _P, _P, _P, _P]),
-    "cmx_ok_solve_f32": (c_int, [_P, _P, _P, c_i64, _P, _P, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_double), c_int, c_double, c_double, _P, _P, _P, _P]),
+    "cmx_ok_solve_workspace_bytes": (c_size_t, [c_i64]),
+    "cmx_ok_solve_f64": (c_int, [_P, _P, _P, c_i64, _P, _P, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_double), c_int, c_double, c_double, _P, _P, _P, _P, c_size_t, _P]),
+    "cmx_ok_solve_f32": (c_int, [_P, _P, _P, c_i64, _P, _P, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_double), c_int, c_double, c_double, _P, _P, _P, _P, c_size_t, _P]),
     "cmx_knn_plan": (c_int, [c_i64, c_i64, c_i64, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
-    "cmx_set_search": (c_int, [c_int]),
     "cmx_copy_rows_to_host": (c_int, [_P, c_size_t, _P, c_size_t, c_size_t, c_size_t, _P]),
-    "cmx_set_output_peers": (c_int, [ctypes.POINTER(ctypes.c_void_p), c_int, c_i64, c_i64]),
-    "cmx_get_search": (c_int, []),
     "cmx_launch_count": (c_i64, []),
     "cmx_reset_launch_count": (None, []),
 }

@@ -8,16 +8,30 @@ namespace cmx {
 namespace {
 thread_local long long g_launches = 0;
 thread_local char g_cuda_err[256] = "";
-thread_local int g_search = CMX_SEARCH_BRUTE;
-thread_local PeerOut g_peer_out = {};
 }  // namespace
 
 void note_launch() { ++g_launches; }
-int search_algorithm() { return g_search; }
-PeerOut take_peer_out() {
-    const PeerOut p = g_peer_out;
-    g_peer_out.n = 0;
-    return p;
+
+int read_options(const cmx_options* opt, int* search, PeerOut* peers) {
+    if (search) *search = CMX_SEARCH_AUTO;
+    if (peers) peers->n = 0;
+    if (!opt) return CMX_OK;
+    if (opt->search != CMX_SEARCH_AUTO && opt->search != CMX_SEARCH_BRUTE && opt->search != CMX_SEARCH_BINNED)
+        return CMX_ERR_BAD_ARG;
+    if (search) *search = opt->search;
+    if (opt->n_peers == 0) return CMX_OK;
+    if (!peers) return CMX_ERR_UNSUPPORTED;  // this entry point has no redirectable output
+    if (opt->n_peers < 0 || opt->n_peers > CMX_MAX_PEERS || opt->m_total < 0 || opt->m_offset < 0 ||
+        opt->m_offset > opt->m_total)
+        return CMX_ERR_BAD_ARG;
+    for (int i = 0; i < opt->n_peers; ++i) {
+        if (!opt->peer_out[i]) return CMX_ERR_BAD_ARG;
+        peers->base[i] = opt->peer_out[i];
+    }
+    peers->n = opt->n_peers;
+    peers->m_total = opt->m_total;
+    peers->m_off = opt->m_offset;
+    return CMX_OK;
 }
 
 int cuda_fail(cudaError_t e) {
@@ -93,7 +107,7 @@ int sm_count() {
 
 extern "C" {
 
-int cmx_version(void) { return 100; }  // 0.1.0
+int cmx_version(void) { return 200; }  // 0.2.0: explicit cmx_options, no per-thread mode
 
 const char* cmx_strerror(int code) {
     switch (code) {
@@ -114,31 +128,6 @@ const char* cmx_last_cuda_error(void) { return cmx::g_cuda_err; }
 int cmx_knn_plan(int64_t n_samples, int64_t n_a, int64_t n_b, int grid, int* tile_rows, int* sample_segments) {
     if (!tile_rows || !sample_segments || n_samples < 0 || n_a < 0 || n_b < 0) return CMX_ERR_BAD_ARG;
     cmx::knn_plan(n_samples, n_a, n_b, grid, tile_rows, sample_segments);
-    return CMX_OK;
-}
-
-int cmx_set_search(int algorithm) {
-    if (algorithm != CMX_SEARCH_BRUTE && algorithm != CMX_SEARCH_BINNED) return CMX_ERR_BAD_ARG;
-    const int prev = cmx::g_search;
-    cmx::g_search = algorithm;
-    return prev;
-}
-int cmx_get_search(void) { return cmx::g_search; }
-
-int cmx_set_output_peers(void* const* peer_out, int n_peers, int64_t m_total, int64_t m_offset) {
-    if (n_peers == 0) {
-        cmx::g_peer_out.n = 0;
-        return CMX_OK;
-    }
-    if (!peer_out || n_peers < 0 || n_peers > CMX_MAX_PEERS || m_total < 0 || m_offset < 0 || m_offset > m_total)
-        return CMX_ERR_BAD_ARG;
-    for (int i = 0; i < n_peers; ++i) {
-        if (!peer_out[i]) return CMX_ERR_BAD_ARG;
-        cmx::g_peer_out.base[i] = peer_out[i];
-    }
-    cmx::g_peer_out.n = n_peers;
-    cmx::g_peer_out.m_total = m_total;
-    cmx::g_peer_out.m_off = m_offset;
     return CMX_OK;
 }
 
@@ -226,9 +215,11 @@ size_t cmx_knn_workspace_bytes_for(int k, int64_t n_samples, int64_t n_a, int64_
 
 int cmx_knn(const double* s_a, const double* s_b, int64_t n, const double* t_a, int64_t n_a, const double* t_b,
             int64_t n_b, int grid, int k, int32_t* idx_out, double* dist_out, void* ws, size_t ws_bytes,
-            void* stream) {
+            const cmx_options* options, void* stream) {
     if (!idx_out) return CMX_ERR_BAD_ARG;
     cmx::KnnJob job{};
+    const int orc = cmx::read_options(options, &job.search, nullptr);
+    if (orc != CMX_OK) return orc;
     job.s_a = s_a;
     job.s_b = s_b;
     job.n = n;

@@ -5,6 +5,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/climatrix_b200.h"
 
 namespace cmx {
@@ -13,16 +15,16 @@ constexpr unsigned kFull = 0xffffffffu;
 
 // ---- host-side bookkeeping (thread-local) ---------------------------------
 void note_launch();                 // ++launch counter
-int search_algorithm();             // CMX_SEARCH_* selected by cmx_set_search on this thread
 
-// Output redirection of the batched IDW kernels (cmx_set_output_peers): the same row segment is stored into the
+// Output redirection of the batched IDW kernels (cmx_options.peer_out): the same row segment is stored into the
 // buffers of up to CMX_MAX_PEERS devices (this one included) at column offset m_off of rows m_total wide.
 struct PeerOut {
     void* base[CMX_MAX_PEERS];
     int n;  // 0: plain output
     long long m_total, m_off;
 };
-PeerOut take_peer_out();            // returns the pending redirection of this thread and clears it
+// validated copy of the caller's options (NULL -> defaults); returns CMX_OK or CMX_ERR_BAD_ARG
+int read_options(const cmx_options* opt, int* search, PeerOut* peers);
 int cuda_fail(cudaError_t e);       // records text, returns CMX_ERR_CUDA
 int check_launch();                 // cudaGetLastError() -> CMX_OK / CMX_ERR_CUDA
 int sm_count();                     // SMs of the current device (cached)
@@ -58,6 +60,7 @@ struct KnnJob {
     void* out;         // [M] (mode 1)
     int k_min;
     double power;
+    int search;        // CMX_SEARCH_AUTO / _BRUTE / _BINNED (cmx_options.search)
     // scratch
     void* workspace;
     size_t workspace_bytes;
@@ -69,6 +72,15 @@ int run_knn(const KnnJob& job, cudaStream_t stream);
 void knn_plan(long long n, long long n_a, long long n_b, int grid, int* tile_rows, int* sample_segments);
 
 // ---- device helpers -----------------------------------------------------------
+// compile-time loop: f(std::integral_constant<int, I>{}) for I in [Begin, End)
+template <int Begin, int End, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (Begin < End) {
+        f(std::integral_constant<int, Begin>{});
+        static_for<Begin + 1, End>(f);
+    }
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -48,16 +48,19 @@ __global__ void __launch_bounds__(BW_THREADS) idw_batch_kernel(
     for (int tl = warp; tl < BW_TARGETS; tl += BW_WARPS) {
         const long long m = m0 + tl;
         double wsum = 0.0;
+        int real = 0;  // neighbours that exist: a short list (NaN sample coordinates) ends in (inf, INT_MAX) sentinels
         for (int j = lane; j < k_use; j += 32) {
             double w = 0.0;
             long long id = 0;
             if (m < M) {
                 const double d = dd[m * k_table + j];
                 id = idx[m * k_table + j];
-                if (id >= 0 && id < n_samples)  // the (inf, INT_MAX) sentinel of a short neighbour list carries no weight
+                if (id >= 0 && id < n_samples) {  // a sentinel carries no weight
                     w = dist_is_squared ? idw_raw_weight(d, power) : idw_weight_from_dist(d, power);
-                else
+                    ++real;
+                } else {
                     id = 0;
+                }
             }
             s_ent[tl * k_use + j].w = w;
             s_ent[tl * k_use + j].off = (unsigned long long)(id * stride_i) * sizeof(V);
@@ -72,7 +75,11 @@ __global__ void __launch_bounds__(BW_THREADS) idw_batch_kernel(
             wn += w;
         }
         wn = warp_sum(wn);
-        if (lane == 0) s_wsum[tl] = wn;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) real += __shfl_xor_sync(kFull, real, o);
+        // fewer than k_min existing neighbours -> NaN also on the path that skips the per-value finiteness test
+        // (a NaN divisor), exactly like the single-slice epilogue (idw.py:179-180)
+        if (lane == 0) s_wsum[tl] = real < k_min ? quiet_nan<double>() : wn;
     }
     __syncthreads();
 
@@ -222,16 +229,19 @@ __global__ void __launch_bounds__(UTHREADS, 5) idw_batch_union_kernel(
     for (int tl = warp; tl < UT; tl += UWARPS) {
         const long long m = m0 + tl;
         double wsum = 0.0;
+        int real = 0;  // neighbours that exist: a short list (NaN sample coordinates) ends in (inf, INT_MAX) sentinels
         for (int j = lane; j < k_use; j += 32) {
             double w = 0.0;
             long long id = 0;
             if (m < M) {
                 const double d = dd[m * k_table + j];
                 id = idx[m * k_table + j];
-                if (id >= 0 && id < n_samples)  // the (inf, INT_MAX) sentinel of a short neighbour list carries no weight
+                if (id >= 0 && id < n_samples) {  // a sentinel carries no weight
                     w = dist_is_squared ? idw_raw_weight(d, power) : idw_weight_from_dist(d, power);
-                else
+                    ++real;
+                } else {
                     id = 0;
+                }
             }
             s_ent[tl * k_use + j].w = w;
             s_ent[tl * k_use + j].off = (unsigned long long)(id * stride_i) * sizeof(V);
@@ -247,7 +257,11 @@ __global__ void __launch_bounds__(UTHREADS, 5) idw_batch_union_kernel(
             wn += w;
         }
         wn = warp_sum(wn);
-        if (lane == 0) s_wsum[tl] = wn;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) real += __shfl_xor_sync(kFull, real, o);
+        // fewer than k_min existing neighbours -> NaN also on the path that skips the per-value finiteness test
+        // (a NaN divisor), exactly like the single-slice epilogue (idw.py:179-180)
+        if (lane == 0) s_wsum[tl] = real < k_min ? quiet_nan<double>() : wn;
     }
     bool use_union = false;
     if (shared_sweep) {
@@ -525,9 +539,12 @@ template <typename V>
 int idw_entry(const double* s_lat, const double* s_lon, int64_t n, const V* vals, int64_t n_batch, int layout,
               const double* t_lat, int64_t n_lat, const double* t_lon, int64_t n_lon, int grid, int k, int k_min,
               double power, V* out, int32_t* idx_out, double* dist_out, void* workspace, size_t workspace_bytes,
-              void* stream_) {
+              const cmx_options* options, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    const PeerOut po = take_peer_out();  // consumed by this call, whatever happens next
+    PeerOut po{};
+    int search = CMX_SEARCH_AUTO;
+    const int orc = read_options(options, &search, &po);
+    if (orc != CMX_OK) return orc;
     if (!vals || !out || n_batch < 1 || k_min < 1) return CMX_ERR_BAD_ARG;
     if (po.n > 0 && n_batch == 1) return CMX_ERR_UNSUPPORTED;
     if (layout != CMX_LAYOUT_BATCH_MAJOR && layout != CMX_LAYOUT_SAMPLE_MAJOR) return CMX_ERR_BAD_ARG;
@@ -549,6 +566,7 @@ int idw_entry(const double* s_lat, const double* s_lon, int64_t n, const V* vals
     job.k_min = k_min;
     job.power = power;
     job.value_is_f32 = sizeof(V) == 4;
+    job.search = search;
     job.workspace = workspace;
     job.workspace_bytes = workspace_bytes;
     if (n_batch == 1) {
@@ -580,8 +598,10 @@ int idw_entry(const double* s_lat, const double* s_lon, int64_t n, const V* vals
 template <typename V>
 int apply_entry(const int32_t* idx, const double* dist, int64_t M, int k_table, const V* vals, int64_t n,
                 int64_t n_batch, int layout, int k_use, int k_min, double power, V* out, int32_t* flag_scratch,
-                void* stream_) {
-    const PeerOut po = take_peer_out();
+                const cmx_options* options, void* stream_) {
+    PeerOut po{};
+    const int orc = read_options(options, nullptr, &po);
+    if (orc != CMX_OK) return orc;
     if (!idx || !dist || !vals || !out) return CMX_ERR_BAD_ARG;
     if (M < 0 || n_batch < 1 || k_use < 1 || k_use > k_table || k_min < 1) return CMX_ERR_BAD_ARG;
     if (k_use > CMX_MAX_K) return CMX_ERR_K_TOO_LARGE;
@@ -605,28 +625,28 @@ size_t cmx_idw_workspace_bytes(int k, int64_t n_targets, int64_t n_batch) {
 int cmx_idw_f64(const double* s_lat, const double* s_lon, int64_t n, const double* vals, int64_t n_batch, int layout,
                 const double* t_lat, int64_t n_lat, const double* t_lon, int64_t n_lon, int grid, int k, int k_min,
                 double power, double* out, int32_t* idx_out, double* dist_out, void* ws, size_t ws_bytes,
-                void* stream) {
+                const cmx_options* options, void* stream) {
     return cmx::idw_entry<double>(s_lat, s_lon, n, vals, n_batch, layout, t_lat, n_lat, t_lon, n_lon, grid, k, k_min,
-                                  power, out, idx_out, dist_out, ws, ws_bytes, stream);
+                                  power, out, idx_out, dist_out, ws, ws_bytes, options, stream);
 }
 int cmx_idw_f32(const double* s_lat, const double* s_lon, int64_t n, const float* vals, int64_t n_batch, int layout,
                 const double* t_lat, int64_t n_lat, const double* t_lon, int64_t n_lon, int grid, int k, int k_min,
                 double power, float* out, int32_t* idx_out, double* dist_out, void* ws, size_t ws_bytes,
-                void* stream) {
+                const cmx_options* options, void* stream) {
     return cmx::idw_entry<float>(s_lat, s_lon, n, vals, n_batch, layout, t_lat, n_lat, t_lon, n_lon, grid, k, k_min,
-                                 power, out, idx_out, dist_out, ws, ws_bytes, stream);
+                                 power, out, idx_out, dist_out, ws, ws_bytes, options, stream);
 }
 int cmx_idw_apply_f64(const int32_t* idx, const double* dist, int64_t M, int k_table, const double* vals, int64_t n,
                       int64_t n_batch, int layout, int k_use, int k_min, double power, double* out,
-                      int32_t* flag_scratch, void* stream) {
+                      int32_t* flag_scratch, const cmx_options* options, void* stream) {
     return cmx::apply_entry<double>(idx, dist, M, k_table, vals, n, n_batch, layout, k_use, k_min, power, out,
-                                    flag_scratch, stream);
+                                    flag_scratch, options, stream);
 }
 int cmx_idw_apply_f32(const int32_t* idx, const double* dist, int64_t M, int k_table, const float* vals, int64_t n,
                       int64_t n_batch, int layout, int k_use, int k_min, double power, float* out,
-                      int32_t* flag_scratch, void* stream) {
+                      int32_t* flag_scratch, const cmx_options* options, void* stream) {
     return cmx::apply_entry<float>(idx, dist, M, k_table, vals, n, n_batch, layout, k_use, k_min, power, out,
-                                   flag_scratch, stream);
+                                   flag_scratch, options, stream);
 }
 
 }  // extern "C"

@@ -140,7 +140,7 @@ __global__ void seed_bbox_kernel(const double* __restrict__ sa, const double* __
     }
 }
 
-__global__ void seed_geometry_kernel(const double* bbox, long long n, SeedGrid* g) {
+__device__ __forceinline__ SeedGrid make_seed_grid(const double* bbox, long long n) {
     const double ea = bbox[1] - bbox[0], eb = bbox[3] - bbox[2];
     SeedGrid s;
     s.a0 = bbox[0];
@@ -162,7 +162,21 @@ __global__ void seed_geometry_kernel(const double* bbox, long long n, SeedGrid* 
     s.ga = ga < 1 ? 1 : (ga > GMAX ? GMAX : ga);
     s.gb = gb < 1 ? 1 : (gb > GMAX ? GMAX : gb);
     s.pad = 0;
-    *g = s;
+    return s;
+}
+
+__global__ void seed_geometry_kernel(const double* bbox, long long n, SeedGrid* g) { *g = make_seed_grid(bbox, n); }
+
+// zero the part of the summed-area table the grid uses ((ga + 1) x (gb + 1) entries of the 2049-wide rows) and,
+// for the binned search, the ga x gb scatter cursors - instead of a 16.8 MB memset regardless of N
+__global__ void seed_clear_kernel(const SeedGrid* g, int* sat, int* cursor) {
+    const int ga = g->ga, gb = g->gb;
+    const long long cells = (long long)(ga + 1) * (gb + 1);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(i / (gb + 1)), col = (int)(i - (long long)row * (gb + 1));
+        sat[(size_t)row * SAT_LD + col] = 0;
+        if (cursor && i < (long long)ga * gb) cursor[i] = 0;
+    }
 }
 
 __device__ __forceinline__ int seed_cell(double x, double x0, double inv_h, int g) {
@@ -795,6 +809,107 @@ __global__ void bin_scatter_kernel(const double* __restrict__ sa, const double* 
     }
 }
 
+// Small sample sets (N <= SMALL_N): the whole pre-pass - bounding box, grid geometry, table clear, histogram,
+// both scans and (for the binned search) the counting-sort scatter - in ONE single-CTA kernel instead of seven
+// launches.  At BASELINE config 1 (N = 1000) the launches, not the work, set the latency of a reconstruct call.
+constexpr int SMALL_N = 16384;
+__global__ void __launch_bounds__(1024) seed_small_kernel(const double* __restrict__ sa, const double* __restrict__ sb,
+                                                          int n, SeedGrid* g, int* sat, int* tile_counter, int* cursor,
+                                                          double* __restrict__ bin_a, double* __restrict__ bin_b,
+                                                          int* __restrict__ bin_idx) {
+    __shared__ double red[4][32];
+    __shared__ SeedGrid sg;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = blockDim.x >> 5;
+    double lo_a = CMX_INF, hi_a = -CMX_INF, lo_b = CMX_INF, hi_b = -CMX_INF;
+    for (int i = tid; i < n; i += nthreads) {
+        const double a = sa[i], b = sb[i];
+        if (isfinite(a) && isfinite(b)) {
+            lo_a = fmin(lo_a, a);
+            hi_a = fmax(hi_a, a);
+            lo_b = fmin(lo_b, b);
+            hi_b = fmax(hi_b, b);
+        }
+    }
+    lo_a = warp_min(lo_a);
+    hi_a = warp_max(hi_a);
+    lo_b = warp_min(lo_b);
+    hi_b = warp_max(hi_b);
+    if (lane == 0) {
+        red[0][warp] = lo_a;
+        red[1][warp] = hi_a;
+        red[2][warp] = lo_b;
+        red[3][warp] = hi_b;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double bbox[4];
+        bbox[0] = warp_min(lane < nwarps ? red[0][lane] : CMX_INF);
+        bbox[1] = warp_max(lane < nwarps ? red[1][lane] : -CMX_INF);
+        bbox[2] = warp_min(lane < nwarps ? red[2][lane] : CMX_INF);
+        bbox[3] = warp_max(lane < nwarps ? red[3][lane] : -CMX_INF);
+        if (lane == 0) {
+            sg = make_seed_grid(bbox, n);
+            *g = sg;
+            *tile_counter = 0;
+        }
+    }
+    __syncthreads();
+    const SeedGrid s = sg;
+    const int ga = s.ga, gb = s.gb;
+    for (int i = tid; i < (ga + 1) * (gb + 1); i += nthreads) {
+        const int row = i / (gb + 1), col = i - row * (gb + 1);
+        sat[(size_t)row * SAT_LD + col] = 0;
+        if (cursor && i < ga * gb) cursor[i] = 0;
+    }
+    __syncthreads();
+    if (s.valid) {
+        for (int i = tid; i < n; i += nthreads) {
+            const double a = sa[i], b = sb[i];
+            if (isfinite(a) && isfinite(b)) {
+                const int ia = seed_cell(a, s.a0, s.inv_h, ga), ib = seed_cell(b, s.b0, s.inv_h, gb);
+                atomicAdd(&sat[(size_t)(ia + 1) * SAT_LD + (ib + 1)], 1);
+            }
+        }
+    }
+    __syncthreads();
+    for (int r = 1 + warp; r <= ga; r += nwarps) {  // inclusive scan along b, one warp per row
+        int* row = sat + (size_t)r * SAT_LD;
+        int carry = 0;
+        for (int c0 = 1; c0 <= gb; c0 += 32) {
+            const int c = c0 + lane;
+            int v = c <= gb ? row[c] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(kFull, v, o);
+                if (lane >= o) v += u;
+            }
+            v += carry;
+            if (c <= gb) row[c] = v;
+            carry = __shfl_sync(kFull, v, 31);
+        }
+    }
+    __syncthreads();
+    for (int c = 1 + tid; c <= gb; c += nthreads) {  // inclusive scan along a, one thread per column
+        int acc = 0;
+        for (int r = 1; r <= ga; ++r) {
+            acc += sat[(size_t)r * SAT_LD + c];
+            sat[(size_t)r * SAT_LD + c] = acc;
+        }
+    }
+    if (!cursor || !s.valid) return;
+    __syncthreads();
+    for (int i = tid; i < n; i += nthreads) {
+        const double a = sa[i], b = sb[i];
+        if (isfinite(a) && isfinite(b)) {
+            const int ia = seed_cell(a, s.a0, s.inv_h, ga), ib = seed_cell(b, s.b0, s.inv_h, gb);
+            const int pos = bin_cell_start(sat, gb, ia, ib) + atomicAdd(&cursor[(size_t)ia * gb + ib], 1);
+            bin_a[pos] = a;
+            bin_b[pos] = b;
+            bin_idx[pos] = i;
+        }
+    }
+}
+
 // seed_bound_d2 evaluated by a whole warp for one target: lane l tests box half-width w_l (0..8, then doubling)
 // in one round, the first lane whose box holds >= k samples wins; the plus-shaped refinement tests 32 arm
 // lengths in a second round and the three far-corner distances are evaluated by lanes 0..2 at once.
@@ -941,19 +1056,20 @@ __global__ void __launch_bounds__(256) knn_binned_kernel(const __grid_constant__
 }
 
 template <int E>
-int launch_binned(const KnnArgs& args, cudaStream_t stream) {
+int launch_binned(const KnnArgs& args, bool scatter, cudaStream_t stream) {
     const int sms = sm_count();
-    const long long pre = (args.j.n + 255) / 256;
-    const int pre_blocks = (int)(pre < (long long)sms * 8 ? pre : (long long)sms * 8);
     timing_begin(CMX_KERNEL_KNN_BINNED, stream);
-    CMX_CUDA(cudaMemsetAsync(args.bin_cursor, 0, (size_t)GMAX * GMAX * sizeof(int), stream));
-    bin_scatter_kernel<<<pre_blocks, 256, 0, stream>>>(args.j.s_a, args.j.s_b, args.j.n, args.seed, args.sat,
-                                                       args.bin_cursor, args.bin_a, args.bin_b, args.bin_idx);
+    if (scatter) {  // (small sample sets: already done by seed_small_kernel; the cursors were cleared by the pre-pass)
+        const long long pre = (args.j.n + 255) / 256;
+        const int pre_blocks = (int)(pre < (long long)sms * 8 ? pre : (long long)sms * 8);
+        bin_scatter_kernel<<<pre_blocks, 256, 0, stream>>>(args.j.s_a, args.j.s_b, args.j.n, args.seed, args.sat,
+                                                           args.bin_cursor, args.bin_a, args.bin_b, args.bin_idx);
+        note_launch();
+    }
     const long long blocks = (args.M * 32 + 255) / 256;
     const long long cap = (long long)sms * 8;
     knn_binned_kernel<E><<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, stream>>>(args);
     timing_end(CMX_KERNEL_KNN_BINNED, stream);
-    note_launch();
     note_launch();
     return check_launch();
 }
@@ -1136,22 +1252,9 @@ int run_knn(const KnnJob& job, cudaStream_t stream) {
     args.seed = seed;
     args.sat = sat;
 
-    // ---- seed grid pre-pass: bbox -> geometry -> histogram -> summed-area table ----
-    const int pre_blocks = (int)((job.n + 255) / 256 < (long long)sms * 8 ? (job.n + 255) / 256 : (long long)sms * 8);
-    seed_init_kernel<<<1, 1, 0, stream>>>(bbox, args.tile_counter);
-    seed_bbox_kernel<<<pre_blocks, 256, 0, stream>>>(job.s_a, job.s_b, job.n, bbox);
-    seed_geometry_kernel<<<1, 1, 0, stream>>>(bbox, job.n, seed);
-    CMX_CUDA(cudaMemsetAsync(sat, 0, (size_t)SAT_LD * SAT_LD * sizeof(int), stream));
-    seed_hist_kernel<<<pre_blocks, 256, 0, stream>>>(job.s_a, job.s_b, job.n, seed, sat);
-    seed_rowscan_kernel<<<GMAX, 32, 0, stream>>>(seed, sat);
-    seed_colscan_kernel<<<(GMAX + 127) / 128, 128, 0, stream>>>(seed, sat);
-    for (int i = 0; i < 6; ++i) note_launch();
-    int rc = check_launch();
-    if (rc != CMX_OK) return rc;
-
-    const int e = list_slots(job.k);
-    if (search_algorithm() == CMX_SEARCH_BINNED) {
-        // K1c borrows K1's (unused) list / candidate scratch: cursors, sorted coordinates, original indices
+    // K1c borrows K1's (unused) list / candidate scratch: cursors, sorted coordinates, original indices
+    bool binned = job.search != CMX_SEARCH_BRUTE;
+    {
         unsigned char* b = ws;
         args.bin_cursor = reinterpret_cast<int*>(b);
         b += (size_t)GMAX * GMAX * sizeof(int);
@@ -1161,13 +1264,35 @@ int run_knn(const KnnJob& job, cudaStream_t stream) {
         b += (size_t)job.n * sizeof(double);
         args.bin_idx = reinterpret_cast<int*>(b);
         b += (size_t)job.n * sizeof(int);
-        if (b <= ws_end) {
-            args.nseg = 1;
-            if (e == 1) return launch_binned<1>(args, stream);
-            if (e == 2) return launch_binned<2>(args, stream);
-            return launch_binned<4>(args, stream);
-        }
-        // does not fit (N beyond ~5e7 with the base workspace): K1 returns the same table
+        if (b > ws_end) binned = false;  // does not fit (N beyond ~5e7 with the base workspace): K1 returns the same table
+    }
+
+    // ---- seed grid pre-pass: bbox -> geometry -> histogram -> summed-area table (-> counting sort) ----
+    const bool small = job.n <= SMALL_N;
+    if (small) {
+        seed_small_kernel<<<1, 1024, 0, stream>>>(job.s_a, job.s_b, (int)job.n, seed, sat, args.tile_counter,
+                                                  binned ? args.bin_cursor : nullptr, args.bin_a, args.bin_b, args.bin_idx);
+        note_launch();
+    } else {
+        const int pre_blocks = (int)((job.n + 255) / 256 < (long long)sms * 8 ? (job.n + 255) / 256 : (long long)sms * 8);
+        seed_init_kernel<<<1, 1, 0, stream>>>(bbox, args.tile_counter);
+        seed_bbox_kernel<<<pre_blocks, 256, 0, stream>>>(job.s_a, job.s_b, job.n, bbox);
+        seed_geometry_kernel<<<1, 1, 0, stream>>>(bbox, job.n, seed);
+        seed_clear_kernel<<<sms * 4, 256, 0, stream>>>(seed, sat, binned ? args.bin_cursor : nullptr);
+        seed_hist_kernel<<<pre_blocks, 256, 0, stream>>>(job.s_a, job.s_b, job.n, seed, sat);
+        seed_rowscan_kernel<<<GMAX, 32, 0, stream>>>(seed, sat);
+        seed_colscan_kernel<<<(GMAX + 127) / 128, 128, 0, stream>>>(seed, sat);
+        for (int i = 0; i < 7; ++i) note_launch();
+    }
+    int rc = check_launch();
+    if (rc != CMX_OK) return rc;
+
+    const int e = list_slots(job.k);
+    if (binned) {
+        args.nseg = 1;
+        if (e == 1) return launch_binned<1>(args, !small, stream);
+        if (e == 2) return launch_binned<2>(args, !small, stream);
+        return launch_binned<4>(args, !small, stream);
     }
 #define CMX_DISPATCH(Q)                                            \
     do {                                                           \

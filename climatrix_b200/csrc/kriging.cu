@@ -28,8 +28,8 @@ constexpr double OK_EPS = 1.0e-10;  // pykrige ok.py: eps
 struct OkArgs {
     const double* s_x;
     const double* s_y;
-    const void* z;
-    int z_is_f32;
+    const double* z;    // [N] standardised values (always float64)
+    int out_is_f32;     // dtype of out / sigmasq
     const int* idx;     // [M][k]
     const double* d2;   // [M][k] exact squared distances (kriging frame)
     long long M;
@@ -43,7 +43,22 @@ struct OkArgs {
     void* out;
     void* sigmasq;
     int* n_singular;
+    // optional work list (the windows the Cholesky kernel handed over): window w of *list_count is target list[w]
+    const int* list;
+    const int* list_count;
 };
+
+__device__ __forceinline__ long long window_count(const OkArgs& a) { return a.list ? (long long)*a.list_count : a.M; }
+__device__ __forceinline__ long long window_target(const OkArgs& a, long long w) { return a.list ? (long long)a.list[w] : w; }
+__device__ __forceinline__ void store_window(const OkArgs& a, long long m, double res, double var) {
+    if (a.out_is_f32) {
+        static_cast<float*>(a.out)[m] = (float)res;
+        if (a.sigmasq) static_cast<float*>(a.sigmasq)[m] = (float)var;
+    } else {
+        static_cast<double*>(a.out)[m] = res;
+        if (a.sigmasq) static_cast<double*>(a.sigmasq)[m] = var;
+    }
+}
 
 // pykrige/variogram_models.py
 __device__ __forceinline__ double gamma_of(int model, double p0, double p1, double p2, double d) {
@@ -77,7 +92,7 @@ __device__ __forceinline__ double sample_distance(int metric, double xi, double 
 }
 
 // E = ceil(k / 32) rows per lane; ld = 32 * E (column stride, in doubles)
-template <int E, typename V>
+template <int E>
 __global__ void __launch_bounds__(256) ok_solve_kernel(const OkArgs a, int warps_per_cta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int LD = 32 * E;
@@ -95,7 +110,9 @@ __global__ void __launch_bounds__(256) ok_solve_kernel(const OkArgs a, int warps
     double* colO = mat + (size_t)(k + 1) * LD;  // right-hand side of ones
 
     const long long total_warps = (long long)gridDim.x * warps_per_cta;
-    for (long long m = (long long)blockIdx.x * warps_per_cta + warp; m < a.M; m += total_warps) {
+    const long long n_windows = window_count(a);
+    for (long long wi = (long long)blockIdx.x * warps_per_cta + warp; wi < n_windows; wi += total_warps) {
+        const long long m = window_target(a, wi);
         // ---- gather the window ----
         double mx[E], my[E], mz[E], borig[E];
 #pragma unroll
@@ -110,7 +127,7 @@ __global__ void __launch_bounds__(256) ok_solve_kernel(const OkArgs a, int warps
                 }
                 mx[e] = a.s_x[id];
                 my[e] = a.s_y[id];
-                mz[e] = a.z_is_f32 ? (double)static_cast<const float*>(a.z)[id] : static_cast<const double*>(a.z)[id];
+                mz[e] = a.z[id];
                 const double bd = window_distance(a.metric, a.d2[m * k + r]);
                 double b = -gamma_of(a.model, a.p0, a.p1, a.p2, bd);
                 if (a.exact_values && fabs(bd) <= OK_EPS) b = 0.0;
@@ -234,8 +251,7 @@ __global__ void __launch_bounds__(256) ok_solve_kernel(const OkArgs a, int warps
                 var = quiet_nan<double>();
                 if (a.n_singular) atomicAdd(a.n_singular, 1);
             }
-            static_cast<V*>(a.out)[m] = (V)res;
-            if (a.sigmasq) static_cast<V*>(a.sigmasq)[m] = (V)var;
+            store_window(a, m, res, var);
         }
         __syncwarp();
     }
@@ -249,7 +265,7 @@ __device__ __forceinline__ void team_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <int W, typename V>
+template <int W>
 __global__ void __launch_bounds__(512) ok_solve_team_kernel(const OkArgs a, int teams_per_cta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int LD = 32 * W;
@@ -273,7 +289,9 @@ __global__ void __launch_bounds__(512) ok_solve_team_kernel(const OkArgs a, int 
     const int bar_id = 1 + team, bar_n = 32 * W;
 
     const long long total_teams = (long long)gridDim.x * teams_per_cta;
-    for (long long m = (long long)blockIdx.x * teams_per_cta + team; m < a.M; m += total_teams) {
+    const long long n_windows = window_count(a);
+    for (long long wi = (long long)blockIdx.x * teams_per_cta + team; wi < n_windows; wi += total_teams) {
+        const long long m = window_target(a, wi);
         double mx = 0.0, my = 0.0, mz = 0.0, borig = 0.0;
         if (r < k) {
             int id = a.idx[m * k + r];
@@ -283,7 +301,7 @@ __global__ void __launch_bounds__(512) ok_solve_team_kernel(const OkArgs a, int 
             }
             mx = a.s_x[id];
             my = a.s_y[id];
-            mz = a.z_is_f32 ? (double)static_cast<const float*>(a.z)[id] : static_cast<const double*>(a.z)[id];
+            mz = a.z[id];
             const double bd = window_distance(a.metric, a.d2[m * k + r]);
             double b = -gamma_of(a.model, a.p0, a.p1, a.p2, bd);
             if (a.exact_values && fabs(bd) <= OK_EPS) b = 0.0;
@@ -393,8 +411,7 @@ __global__ void __launch_bounds__(512) ok_solve_team_kernel(const OkArgs a, int 
                 var = quiet_nan<double>();
                 if (a.n_singular) atomicAdd(a.n_singular, 1);
             }
-            static_cast<V*>(a.out)[m] = (V)res;
-            if (a.sigmasq) static_cast<V*>(a.sigmasq)[m] = (V)var;
+            store_window(a, m, res, var);
         }
         team_sync(bar_id, bar_n);  // shared memory of the team is reused by the next window
     }
@@ -611,7 +628,9 @@ __global__ void __launch_bounds__(TEAMS * ((KC + 31) / 32) * 32, KC > 32 ? 3 : 4
     const VarioConst vc = vario_const(A.model, A.p0, A.p1, A.p2);
 
     const long long total_teams = (long long)gridDim.x * TEAMS;
-    for (long long m = (long long)blockIdx.x * TEAMS + team; m < A.M; m += total_teams) {
+    const long long n_windows = window_count(A);
+    for (long long wi = (long long)blockIdx.x * TEAMS + team; wi < n_windows; wi += total_teams) {
+        const long long m = window_target(A, wi);
         double mx = 0.0, my = 0.0, mz = 0.0, borig = 0.0;
         if (r < k) {
             int id = A.idx[m * k + r];
@@ -621,7 +640,7 @@ __global__ void __launch_bounds__(TEAMS * ((KC + 31) / 32) * 32, KC > 32 ? 3 : 4
             }
             mx = A.s_x[id];
             my = A.s_y[id];
-            mz = A.z_is_f32 ? (double)static_cast<const float*>(A.z)[id] : static_cast<const double*>(A.z)[id];
+            mz = A.z[id];
             const double bd = window_distance(A.metric, A.d2[m * k + r]);
             double b = -gamma_pre(vc, bd);
             if (A.exact_values && fabs(bd) <= OK_EPS) b = 0.0;
@@ -717,16 +736,27 @@ __global__ void __launch_bounds__(TEAMS * ((KC + 31) / 32) * 32, KC > 32 ? 3 : 4
                 var = quiet_nan<double>();
                 if (A.n_singular) atomicAdd(A.n_singular, 1);
             }
-            if (A.z_is_f32) {  // output dtype follows the value dtype
-                static_cast<float*>(A.out)[m] = (float)res;
-                if (A.sigmasq) static_cast<float*>(A.sigmasq)[m] = (float)var;
-            } else {
-                static_cast<double*>(A.out)[m] = res;
-                if (A.sigmasq) static_cast<double*>(A.sigmasq)[m] = var;
-            }
+            store_window(A, m, res, var);
         }
         team_barrier();  // the team's shared memory is reused by the next window
     }
+}
+
+}  // namespace
+}  // namespace cmx
+
+#include "ok_chol.cuh"
+
+namespace cmx {
+namespace {
+
+// grid of a pivoted kernel: all windows, or - on the hand-over list, whose length only the device knows - a
+// modest persistent grid (the list is normally empty or short)
+inline long long pivoted_ctas(const OkArgs& a, int windows_per_cta, int ctas_per_sm) {
+    const long long cap = (long long)sm_count() * ctas_per_sm;
+    if (a.list) return cap < 2LL * sm_count() ? cap : 2LL * sm_count();
+    const long long ctas = (a.M + windows_per_cta - 1) / windows_per_cta;
+    return ctas > cap ? cap : ctas;
 }
 
 template <int KC>
@@ -735,17 +765,13 @@ int launch_ok_rows(const OkArgs& a, cudaStream_t stream) {
     constexpr int TEAMS = NW == 1 ? 4 : 2;  // 128 threads per CTA
     const size_t smem = TEAMS * ((rows_team_smem<KC>() + 15) & ~size_t(15));
     CMX_CUDA(cudaFuncSetAttribute(ok_solve_rows_kernel<KC, TEAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long ctas = (a.M + TEAMS - 1) / TEAMS;
-    const long long cap = (long long)sm_count() * 8;
-    if (ctas > cap) ctas = cap;
-    timing_begin(CMX_KERNEL_OK_SOLVE, stream);
+    const long long ctas = pivoted_ctas(a, TEAMS, 8);
     ok_solve_rows_kernel<KC, TEAMS><<<(unsigned)ctas, TEAMS * NW * 32, smem, stream>>>(a);
-    timing_end(CMX_KERNEL_OK_SOLVE, stream);
     note_launch();
     return check_launch();
 }
 
-template <int W, typename V>
+template <int W>
 int launch_ok_team(const OkArgs& a, cudaStream_t stream) {
     const int k = a.k;
     const size_t per_team = (size_t)(k + 2) * 32 * W * sizeof(double) + 2 * 32 * W * sizeof(double) + 32 * W * sizeof(int) +
@@ -754,46 +780,55 @@ int launch_ok_team(const OkArgs& a, cudaStream_t stream) {
     const int max_teams = 512 / (32 * W) < 15 ? 512 / (32 * W) : 15;  // <= 16 warps per CTA, <= 15 named barriers
     teams = teams > max_teams ? max_teams : (teams < 1 ? 1 : teams);
     const size_t smem = per_team * teams;
-    CMX_CUDA(cudaFuncSetAttribute(ok_solve_team_kernel<W, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long ctas = (a.M + teams - 1) / teams;
-    const long long cap = (long long)sm_count() * 4;
-    if (ctas > cap) ctas = cap;
-    timing_begin(CMX_KERNEL_OK_SOLVE, stream);
-    ok_solve_team_kernel<W, V><<<(unsigned)ctas, teams * W * 32, smem, stream>>>(a, teams);
-    timing_end(CMX_KERNEL_OK_SOLVE, stream);
+    CMX_CUDA(cudaFuncSetAttribute(ok_solve_team_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long ctas = pivoted_ctas(a, teams, 4);
+    ok_solve_team_kernel<W><<<(unsigned)ctas, teams * W * 32, smem, stream>>>(a, teams);
     note_launch();
     return check_launch();
 }
 
-template <int E, typename V>
+template <int E>
 int launch_ok(const OkArgs& a, cudaStream_t stream) {
     const int k = a.k;
     const size_t per_warp = (size_t)(k + 2) * 32 * E * sizeof(double) + 2 * 32 * E * sizeof(double) + 32 * E * sizeof(int);
     int warps = (int)((200 * 1024) / per_warp);
     warps = warps > 8 ? 8 : (warps < 1 ? 1 : warps);
     const size_t smem = per_warp * warps;
-    CMX_CUDA(cudaFuncSetAttribute(ok_solve_kernel<E, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long ctas = (a.M + warps - 1) / warps;
-    const long long cap = (long long)sm_count() * 8;
-    if (ctas > cap) ctas = cap;
-    timing_begin(CMX_KERNEL_OK_SOLVE, stream);
-    ok_solve_kernel<E, V><<<(unsigned)ctas, warps * 32, smem, stream>>>(a, warps);
-    timing_end(CMX_KERNEL_OK_SOLVE, stream);
+    CMX_CUDA(cudaFuncSetAttribute(ok_solve_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long ctas = pivoted_ctas(a, warps, 8);
+    ok_solve_kernel<E><<<(unsigned)ctas, warps * 32, smem, stream>>>(a, warps);
     note_launch();
     return check_launch();
 }
 
-// K4 on an existing neighbour table
-template <typename V>
-int solve_table(const double* s_x, const double* s_y, const V* z, long long n, const int* idx, const double* d2,
+// Gauss-Jordan with partial pivoting: all windows of `a`, or the windows on a.list
+int launch_pivoted(const OkArgs& a, cudaStream_t stream) {
+    const int k = a.k;
+#ifndef CMX_OK_SMEM_ONLY
+    if (k <= 16) return launch_ok_rows<16>(a, stream);
+    if (k <= 32) return launch_ok_rows<32>(a, stream);
+    if (k <= 48) return launch_ok_rows<48>(a, stream);
+    if (k <= 64) return launch_ok_rows<64>(a, stream);
+#endif
+    if (k <= 32) return launch_ok<1>(a, stream);
+    if (k <= 64) return launch_ok_team<2>(a, stream);
+    return launch_ok_team<4>(a, stream);
+}
+
+inline size_t chol_scratch_bytes(long long M) { return ((size_t)(M > 0 ? M : 0) * sizeof(int) + 256 + 255) & ~size_t(255); }
+
+// K4 on an existing neighbour table.  scratch (chol_scratch_bytes(M), may be null): hand-over list of the Cholesky path.
+int solve_table(const double* s_x, const double* s_y, const double* z, long long n, const int* idx, const double* d2,
                 long long M, int metric, int k, int model, const double* params, int exact_values, double out_scale,
-                double out_shift, V* out, V* sigmasq, int32_t* n_singular, cudaStream_t stream) {
+                double out_shift, void* out, void* sigmasq, int out_is_f32, int32_t* n_singular, void* scratch,
+                size_t scratch_bytes, cudaStream_t stream) {
     if (M == 0) return CMX_OK;
+    if (M > 0x7fffffffLL) return CMX_ERR_TOO_MANY;
     OkArgs a;
     a.s_x = s_x;
     a.s_y = s_y;
     a.z = z;
-    a.z_is_f32 = sizeof(V) == 4;
+    a.out_is_f32 = out_is_f32;
     a.idx = idx;
     a.d2 = d2;
     a.M = M;
@@ -810,35 +845,55 @@ int solve_table(const double* s_x, const double* s_y, const V* z, long long n, c
     a.out = out;
     a.sigmasq = sigmasq;
     a.n_singular = n_singular;
-#ifndef CMX_OK_SMEM_ONLY
-    if (k <= 16) return launch_ok_rows<16>(a, stream);
-    if (k <= 32) return launch_ok_rows<32>(a, stream);
-    if (k <= 48) return launch_ok_rows<48>(a, stream);
-    if (k <= 64) return launch_ok_rows<64>(a, stream);
+    a.list = nullptr;
+    a.list_count = nullptr;
+    timing_begin(CMX_KERNEL_OK_SOLVE, stream);
+    int rc;
+#ifndef CMX_OK_NO_CHOL
+    if (k >= 2 && k <= 64 && scratch && scratch_bytes >= chol_scratch_bytes(M)) {
+        unsigned char* sc = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(scratch) + 255) & ~uintptr_t(255));
+        if (sc + 256 + (size_t)M * sizeof(int) > static_cast<unsigned char*>(scratch) + scratch_bytes) return CMX_ERR_WORKSPACE;
+        int* fail_count = reinterpret_cast<int*>(sc);
+        int* fail_list = reinterpret_cast<int*>(sc + 256);
+        CMX_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(int), stream));
+        if (k <= 16) rc = launch_ok_chol<2>(a, fail_list, fail_count, stream);
+        else if (k <= 32) rc = launch_ok_chol<4>(a, fail_list, fail_count, stream);
+        else if (k <= 48) rc = launch_ok_chol<6>(a, fail_list, fail_count, stream);
+        else rc = launch_ok_chol<8>(a, fail_list, fail_count, stream);
+        if (rc == CMX_OK) {
+            a.list = fail_list;
+            a.list_count = fail_count;
+            rc = launch_pivoted(a, stream);
+        }
+    } else
 #endif
-    if (k <= 32) return launch_ok<1, V>(a, stream);
-    if (k <= 64) return launch_ok_team<2, V>(a, stream);
-    return launch_ok_team<4, V>(a, stream);
+    {
+        rc = launch_pivoted(a, stream);
+    }
+    timing_end(CMX_KERNEL_OK_SOLVE, stream);
+    return rc;
 }
 
-template <typename V>
-int solve_entry(const double* s_x, const double* s_y, const V* z, int64_t n, const int32_t* idx, const double* d2,
+int solve_entry(const double* s_x, const double* s_y, const double* z, int64_t n, const int32_t* idx, const double* d2,
                 int64_t M, int metric, int k, int model, const double* params, int exact_values, double out_scale,
-                double out_shift, V* out, V* sigmasq, int32_t* n_singular, void* stream) {
+                double out_shift, void* out, void* sigmasq, int out_is_f32, int32_t* n_singular, void* ws,
+                size_t ws_bytes, void* stream) {
     if (!s_x || !s_y || !z || !idx || !d2 || !params || !out || n < 1 || M < 0 || k < 1) return CMX_ERR_BAD_ARG;
     if (k > CMX_MAX_K) return CMX_ERR_K_TOO_LARGE;
     if (model < CMX_VARIOGRAM_LINEAR || model > CMX_VARIOGRAM_EXPONENTIAL) return CMX_ERR_UNSUPPORTED;
     if (metric != CMX_METRIC_EUCLIDEAN && metric != CMX_METRIC_GEOGRAPHIC) return CMX_ERR_UNSUPPORTED;
-    return solve_table<V>(s_x, s_y, z, n, idx, d2, M, metric, k, model, params, exact_values, out_scale, out_shift,
-                          out, sigmasq, n_singular, static_cast<cudaStream_t>(stream));
+    return solve_table(s_x, s_y, z, n, idx, d2, M, metric, k, model, params, exact_values, out_scale, out_shift, out,
+                       sigmasq, out_is_f32, n_singular, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
-template <typename V>
-int ok_entry(const double* s_x, const double* s_y, const V* z, int64_t n, const double* t_x, int64_t n_x,
+int ok_entry(const double* s_x, const double* s_y, const double* z, int64_t n, const double* t_x, int64_t n_x,
              const double* t_y, int64_t n_y, int grid, int metric, int k, int model, const double* params,
-             int exact_values, double out_scale, double out_shift, V* out, V* sigmasq, int32_t* n_singular,
-             void* workspace, size_t workspace_bytes, void* stream_) {
+             int exact_values, double out_scale, double out_shift, void* out, void* sigmasq, int out_is_f32,
+             int32_t* n_singular, void* workspace, size_t workspace_bytes, const cmx_options* options, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    int search = CMX_SEARCH_AUTO;
+    const int orc = read_options(options, &search, nullptr);
+    if (orc != CMX_OK) return orc;
     if (!s_x || !s_y || !z || !t_x || !t_y || !params || !out) return CMX_ERR_BAD_ARG;
     if (model < CMX_VARIOGRAM_LINEAR || model > CMX_VARIOGRAM_EXPONENTIAL) return CMX_ERR_UNSUPPORTED;
     if (metric != CMX_METRIC_EUCLIDEAN) return CMX_ERR_UNSUPPORTED;  // geographic: cmx_knn3 + cmx_ok_solve_*
@@ -846,13 +901,15 @@ int ok_entry(const double* s_x, const double* s_y, const V* z, int64_t n, const 
     if (k > CMX_MAX_K) return CMX_ERR_K_TOO_LARGE;
     if (n_x < 0 || n_y < 0) return CMX_ERR_BAD_ARG;
     const long long M = grid ? (long long)n_x * n_y : (long long)n_x;
-    // workspace: [neighbour table | kNN scratch]
+    // workspace: [neighbour table | hand-over list | kNN scratch]
     if (!workspace || workspace_bytes < cmx_ok_workspace_bytes(k, M)) return CMX_ERR_WORKSPACE;
     const size_t tab_bytes = ((size_t)M * k * (sizeof(double) + sizeof(int)) + 255) & ~size_t(255);
+    const size_t list_bytes = chol_scratch_bytes(M);
     unsigned char* extra = static_cast<unsigned char*>(workspace);
     extra = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(extra) + 255) & ~uintptr_t(255));
     double* d2_tab = reinterpret_cast<double*>(extra);
     int* idx_tab = reinterpret_cast<int*>(extra + (size_t)M * k * sizeof(double));
+    unsigned char* list_scratch = extra + tab_bytes;
 
     // neighbours in the kriging frame: rows of a dense target grid run along y (lat), columns along x (lon)
     KnnJob job{};
@@ -867,14 +924,15 @@ int ok_entry(const double* s_x, const double* s_y, const V* z, int64_t n, const 
     job.k = k;
     job.idx_out = idx_tab;
     job.d2_out = d2_tab;
-    job.workspace = extra + tab_bytes;
-    job.workspace_bytes = workspace_bytes - (size_t)((extra + tab_bytes) - static_cast<unsigned char*>(workspace));
+    job.search = search;
+    job.workspace = list_scratch + list_bytes;
+    job.workspace_bytes = workspace_bytes - (size_t)((list_scratch + list_bytes) - static_cast<unsigned char*>(workspace));
     int rc = run_knn(job, stream);
     if (rc != CMX_OK) return rc;
     if (M == 0) return CMX_OK;
 
-    return solve_table<V>(s_x, s_y, z, n, idx_tab, d2_tab, M, CMX_METRIC_EUCLIDEAN, k, model, params, exact_values,
-                          out_scale, out_shift, out, sigmasq, n_singular, stream);
+    return solve_table(s_x, s_y, z, n, idx_tab, d2_tab, M, CMX_METRIC_EUCLIDEAN, k, model, params, exact_values,
+                       out_scale, out_shift, out, sigmasq, out_is_f32, n_singular, list_scratch, list_bytes, stream);
 }
 
 }  // namespace
@@ -882,38 +940,41 @@ int ok_entry(const double* s_x, const double* s_y, const V* z, int64_t n, const 
 
 extern "C" {
 
+size_t cmx_ok_solve_workspace_bytes(int64_t n_targets) { return cmx::chol_scratch_bytes(n_targets) + 256; }
+
 size_t cmx_ok_workspace_bytes(int k, int64_t n_targets) {
     if (k < 1 || k > CMX_MAX_K || n_targets < 0) return 0;
-    return cmx::knn_workspace_bytes(k) + (size_t)n_targets * (size_t)k * (sizeof(double) + sizeof(int)) + 2048;
+    return cmx::knn_workspace_bytes(k) + (size_t)n_targets * (size_t)k * (sizeof(double) + sizeof(int)) +
+           cmx::chol_scratch_bytes(n_targets) + 2048;
 }
 
 int cmx_ok_mw_f64(const double* s_x, const double* s_y, const double* z, int64_t n, const double* t_x, int64_t n_x,
                   const double* t_y, int64_t n_y, int grid, int metric, int k, int model, const double params[3],
                   int exact_values, double out_scale, double out_shift, double* out, double* sigmasq,
-                  int32_t* n_singular, void* ws, size_t ws_bytes, void* stream) {
-    return cmx::ok_entry<double>(s_x, s_y, z, n, t_x, n_x, t_y, n_y, grid, metric, k, model, params, exact_values,
-                                 out_scale, out_shift, out, sigmasq, n_singular, ws, ws_bytes, stream);
+                  int32_t* n_singular, void* ws, size_t ws_bytes, const cmx_options* options, void* stream) {
+    return cmx::ok_entry(s_x, s_y, z, n, t_x, n_x, t_y, n_y, grid, metric, k, model, params, exact_values, out_scale,
+                         out_shift, out, sigmasq, 0, n_singular, ws, ws_bytes, options, stream);
+}
+int cmx_ok_mw_f32(const double* s_x, const double* s_y, const double* z, int64_t n, const double* t_x, int64_t n_x,
+                  const double* t_y, int64_t n_y, int grid, int metric, int k, int model, const double params[3],
+                  int exact_values, double out_scale, double out_shift, float* out, float* sigmasq,
+                  int32_t* n_singular, void* ws, size_t ws_bytes, const cmx_options* options, void* stream) {
+    return cmx::ok_entry(s_x, s_y, z, n, t_x, n_x, t_y, n_y, grid, metric, k, model, params, exact_values, out_scale,
+                         out_shift, out, sigmasq, 1, n_singular, ws, ws_bytes, options, stream);
 }
 int cmx_ok_solve_f64(const double* s_x, const double* s_y, const double* z, int64_t n, const int32_t* idx,
                      const double* d2, int64_t M, int metric, int k, int model, const double params[3],
                      int exact_values, double out_scale, double out_shift, double* out, double* sigmasq,
-                     int32_t* n_singular, void* stream) {
-    return cmx::solve_entry<double>(s_x, s_y, z, n, idx, d2, M, metric, k, model, params, exact_values, out_scale,
-                                    out_shift, out, sigmasq, n_singular, stream);
+                     int32_t* n_singular, void* ws, size_t ws_bytes, void* stream) {
+    return cmx::solve_entry(s_x, s_y, z, n, idx, d2, M, metric, k, model, params, exact_values, out_scale, out_shift,
+                            out, sigmasq, 0, n_singular, ws, ws_bytes, stream);
 }
-int cmx_ok_solve_f32(const double* s_x, const double* s_y, const float* z, int64_t n, const int32_t* idx,
+int cmx_ok_solve_f32(const double* s_x, const double* s_y, const double* z, int64_t n, const int32_t* idx,
                      const double* d2, int64_t M, int metric, int k, int model, const double params[3],
                      int exact_values, double out_scale, double out_shift, float* out, float* sigmasq,
-                     int32_t* n_singular, void* stream) {
-    return cmx::solve_entry<float>(s_x, s_y, z, n, idx, d2, M, metric, k, model, params, exact_values, out_scale,
-                                   out_shift, out, sigmasq, n_singular, stream);
-}
-int cmx_ok_mw_f32(const double* s_x, const double* s_y, const float* z, int64_t n, const double* t_x, int64_t n_x,
-                  const double* t_y, int64_t n_y, int grid, int metric, int k, int model, const double params[3],
-                  int exact_values, double out_scale, double out_shift, float* out, float* sigmasq,
-                  int32_t* n_singular, void* ws, size_t ws_bytes, void* stream) {
-    return cmx::ok_entry<float>(s_x, s_y, z, n, t_x, n_x, t_y, n_y, grid, metric, k, model, params, exact_values,
-                                out_scale, out_shift, out, sigmasq, n_singular, ws, ws_bytes, stream);
+                     int32_t* n_singular, void* ws, size_t ws_bytes, void* stream) {
+    return cmx::solve_entry(s_x, s_y, z, n, idx, d2, M, metric, k, model, params, exact_values, out_scale, out_shift,
+                            out, sigmasq, 1, n_singular, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

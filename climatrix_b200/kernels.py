@@ -120,17 +120,19 @@ def reset_launch_count() -> None:
 
 KERNEL_KNN, KERNEL_IDW_BATCH, KERNEL_OK_SOLVE, KERNEL_KNN_BINNED = 0, 1, 2, 3
 
-SEARCH_ALGORITHMS = {"brute": 0, "binned": 1}
-_search = "brute"
+SEARCH_ALGORITHMS = {"auto": _lib.SEARCH_AUTO, "brute": _lib.SEARCH_BRUTE, "binned": _lib.SEARCH_BINNED}
+_search = "auto"
 
 
 def set_search(algorithm: str) -> str:
-    """Choose the planar neighbour search for all following calls of this process; returns the previous one.
+    """Default planar neighbour search of this process (every call can also name one); returns the previous one.
 
-    ``"brute"`` (default): K1, every (target, sample) pair is evaluated - the brute-force kernel of the
-    north_star.  ``"binned"``: K1c, samples counting-sorted into grid cells, each target scans only the
-    cells its k-th-distance bound touches (the role cKDTree's pruning plays in ``reconstruct/idw.py:155-158``).
-    Both produce identical neighbour tables.
+    ``"auto"`` (default): the faster algorithm for the problem - the cell-binned search whenever its scratch fits.
+    ``"brute"``: K1, every (target, sample) pair is evaluated - the brute-force kernel of the north_star.
+    ``"binned"``: K1c, samples counting-sorted into grid cells, each target scans only the cells its
+    k-th-distance bound touches (the role cKDTree's pruning plays in ``reconstruct/idw.py:155-158``).
+    All produce identical neighbour tables.  The choice travels to the library as an explicit per-call
+    argument (``cmx_options.search``); the library itself keeps no mode.
     """
     global _search
     if algorithm not in SEARCH_ALGORITHMS:
@@ -143,9 +145,24 @@ def get_search() -> str:
     return _search
 
 
-def _apply_search(lib) -> None:
-    # the library setting is per thread; the Python setting is per process
-    lib.cmx_set_search(SEARCH_ALGORITHMS[_search])
+def _options(search: str | None = None, peer_out: tuple | None = None):
+    """``cmx_options`` for one call: search algorithm (None -> the process default) and, optionally, the
+    peer buffers ``(pointers, m_total, m_offset)`` the batched IDW kernels store into."""
+    search = _search if search is None else search
+    if search not in SEARCH_ALGORITHMS:
+        raise ValueError(f"unknown search algorithm {search!r}; choose from {sorted(SEARCH_ALGORITHMS)}")
+    opt = _lib.Options()
+    opt.search = SEARCH_ALGORITHMS[search]
+    opt.n_peers = 0
+    if peer_out is not None:
+        ptrs, m_total, m_off = peer_out
+        if not 1 <= len(ptrs) <= _lib.MAX_PEERS:
+            raise ValueError(f"peer_out needs 1..{_lib.MAX_PEERS} buffers")
+        opt.n_peers = len(ptrs)
+        for i, q in enumerate(ptrs):
+            opt.peer_out[i] = int(q)
+        opt.m_total, opt.m_offset = int(m_total), int(m_off)
+    return ctypes.byref(opt)
 
 
 def kernel_timing(enable: bool) -> None:
@@ -181,14 +198,14 @@ def _check_samples(s_lat, s_lon):
         )
 
 
-def knn(s_lat, s_lon, targets: Targets, k: int, *, return_distance: bool = True):
+def knn(s_lat, s_lon, targets: Targets, k: int, *, return_distance: bool = True, search: str | None = None):
     """k nearest samples of every target: ``(dist (M,k) f64 | None, idx (M,k) int32)``.
 
     Replaces ``cKDTree(points).query(targets, k, workers=-1)`` (idw.py:155-158):
     Euclidean in the flat (lat, lon) plane, rows ascending by (distance, index).
     """
     lib = _lib.load()
-    _apply_search(lib)
+    opt = _options(search)
     dev = _require_cuda(targets.lat.device)
     s_lat, s_lon = _as_f64(s_lat, dev), _as_f64(s_lon, dev)
     _check_samples(s_lat, s_lon)
@@ -200,7 +217,7 @@ def knn(s_lat, s_lon, targets: Targets, k: int, *, return_distance: bool = True)
         ws = _workspace(_knn_ws_bytes(lib, k, s_lat.numel(), targets), dev)
         rc = lib.cmx_knn(_ptr(s_lat), _ptr(s_lon), s_lat.numel(), _ptr(targets.lat), targets.lat.numel(),
                          _ptr(targets.lon), targets.lon.numel(), int(targets.grid), k, _ptr(idx), _ptr(dist),
-                         _ptr(ws), ws.numel(), _stream())
+                         _ptr(ws), ws.numel(), opt, _stream())
     _lib.check(rc, "cmx_knn")
     return dist, idx
 
@@ -228,7 +245,7 @@ def _values_layout(values: torch.Tensor, n: int, layout: str | None):
 
 def idw(s_lat, s_lon, values, targets: Targets, *, k: int = 5, power: float = 2.0, k_min: int = 2,
         dtype: torch.dtype = torch.float64, layout: str | None = None, return_neighbours: bool = False,
-        out: torch.Tensor | None = None, peer_out: tuple | None = None):
+        out: torch.Tensor | None = None, peer_out: tuple | None = None, search: str | None = None):
     """Inverse-distance weighting on the device (reference idw.py:155-180).
 
     ``values``: (N,) one slice, or a time/level batch as (T, N) ("batch_major") or
@@ -240,7 +257,6 @@ def idw(s_lat, s_lon, values, targets: Targets, *, k: int = 5, power: float = 2.
     memory, see ``sharding.PeerGather``); nothing is returned in that case.
     """
     lib = _lib.load()
-    _apply_search(lib)
     dev = _require_cuda(targets.lat.device)
     if dtype not in (torch.float64, torch.float32):
         raise TypeError("dtype must be torch.float64 or torch.float32")
@@ -249,7 +265,8 @@ def idw(s_lat, s_lon, values, targets: Targets, *, k: int = 5, power: float = 2.
     n = s_lat.numel()
     if not isinstance(values, torch.Tensor):
         values = torch.as_tensor(np.ascontiguousarray(values))
-    if values.device.type == "cpu" and values.dim() == 2 and values.numel() >= (1 << 22) and out is None:
+    if (values.device.type == "cpu" and values.dim() == 2 and values.numel() >= (1 << 22) and out is None
+            and peer_out is None):
         # Host-resident batch: the values are only needed by the weighting kernel, so their host->device
         # copy runs on a side stream while the neighbour search (which needs coordinates only) computes.
         with torch.cuda.device(dev):
@@ -257,7 +274,7 @@ def idw(s_lat, s_lon, values, targets: Targets, *, k: int = 5, power: float = 2.
             side = torch.cuda.Stream(dev)
             # search first: the launch is asynchronous, whereas a copy from pageable host memory keeps the host
             # busy staging - so the upload below really runs while the search kernel computes
-            dist, idx = knn(s_lat, s_lon, targets, k)
+            dist, idx = knn(s_lat, s_lon, targets, k, search=search)
             with torch.cuda.stream(side):
                 vals_d = values.to(device=dev, dtype=dtype, non_blocking=True)
             main.wait_stream(side)
@@ -274,11 +291,8 @@ def idw(s_lat, s_lon, values, targets: Targets, *, k: int = 5, power: float = 2.
     m = targets.count
     with torch.cuda.device(dev):
         if peer_out is not None:
-            ptrs, m_total, m_off = peer_out
             if n_batch < 2 or return_neighbours:
                 raise ValueError("peer_out needs a batch of at least two slices and no neighbour output")
-            arr = (ctypes.c_void_p * len(ptrs))(*[int(q) for q in ptrs])
-            _lib.check(lib.cmx_set_output_peers(arr, len(ptrs), int(m_total), int(m_off)), "cmx_set_output_peers")
             out = torch.empty(1, dtype=dtype, device=dev)  # placeholder: the call's own output argument is unused
         elif out is None:
             out = torch.empty((n_batch, m) if n_batch > 1 or values.dim() == 2 else (m,), dtype=dtype, device=dev)
@@ -293,7 +307,8 @@ def idw(s_lat, s_lon, values, targets: Targets, *, k: int = 5, power: float = 2.
         fn = lib.cmx_idw_f64 if dtype == torch.float64 else lib.cmx_idw_f32
         rc = fn(_ptr(s_lat), _ptr(s_lon), n, _ptr(values), n_batch, layout_code, _ptr(targets.lat),
                 targets.lat.numel(), _ptr(targets.lon), targets.lon.numel(), int(targets.grid), k, k_min,
-                float(power), _ptr(out), _ptr(idx), _ptr(dist), _ptr(ws), ws.numel(), _stream())
+                float(power), _ptr(out), _ptr(idx), _ptr(dist), _ptr(ws), ws.numel(), _options(search, peer_out),
+                _stream())
     _lib.check(rc, "cmx_idw")
     if peer_out is not None:
         return None
@@ -327,7 +342,7 @@ def idw_apply(idx: torch.Tensor, dist: torch.Tensor, values, *, k: int | None = 
         flag = torch.zeros(1, dtype=torch.int32, device=dev) if n_batch > 1 else None
         fn = lib.cmx_idw_apply_f64 if dtype == torch.float64 else lib.cmx_idw_apply_f32
         rc = fn(_ptr(idx.contiguous()), _ptr(dist.contiguous()), m, k_table, _ptr(values), n, n_batch, layout_code,
-                k, int(k_min), float(power), _ptr(out), _ptr(flag), _stream())
+                k, int(k_min), float(power), _ptr(out), _ptr(flag), None, _stream())
     _lib.check(rc, "cmx_idw_apply")
     return out
 
@@ -367,20 +382,22 @@ def empirical_variogram(x, y, z, nlags: int, *, geographic: bool = False):
 
 def ok_moving_window(s_x, s_y, z, t_x, t_y, grid: bool, *, k: int, variogram_model: str, params,
                      geographic: bool = False, exact_values: bool = True, out_scale: float = 1.0,
-                     out_shift: float = 0.0, dtype: torch.dtype = torch.float64, return_sigmasq: bool = False):
+                     out_shift: float = 0.0, dtype: torch.dtype = torch.float64, return_sigmasq: bool = False,
+                     search: str | None = None):
     """Moving-window ordinary kriging in the (already normalised / anisotropy-adjusted) frame.
 
     pykrige ``execute(style, xpoints, ypoints, backend="loop", n_closest_points=k)``.
-    Grid targets: x = columns (n_x), y = rows (n_y); output (n_y * n_x,).
+    Grid targets: x = columns (n_x), y = rows (n_y); output (n_y * n_x,).  ``dtype`` is the dtype the field
+    (and the variance) is stored in; the standardised values ``z`` and all arithmetic are float64.
     """
     lib = _lib.load()
-    _apply_search(lib)
+    opt = _options(search)
     dev = _require_cuda(s_x.device if isinstance(s_x, torch.Tensor) else None)
     s_x, s_y = _as_f64(s_x, dev), _as_f64(s_y, dev)
     t_x, t_y = _as_f64(t_x, dev), _as_f64(t_y, dev)
     if not isinstance(z, torch.Tensor):
         z = torch.as_tensor(np.ascontiguousarray(z))
-    z = z.to(device=dev, dtype=dtype).contiguous()
+    z = z.to(device=dev, dtype=torch.float64).contiguous()
     n = s_x.numel()
     m = t_x.numel() * t_y.numel() if grid else t_x.numel()
     if not grid and t_x.numel() != t_y.numel():
@@ -398,7 +415,8 @@ def ok_moving_window(s_x, s_y, z, t_x, t_y, grid: bool, *, k: int, variogram_mod
         fn = lib.cmx_ok_mw_f64 if dtype == torch.float64 else lib.cmx_ok_mw_f32
         rc = fn(_ptr(s_x), _ptr(s_y), _ptr(z), n, _ptr(t_x), t_x.numel(), _ptr(t_y), t_y.numel(), int(grid),
                 _lib.METRIC_GEOGRAPHIC if geographic else _lib.METRIC_EUCLIDEAN, k, model, p, int(exact_values),
-                float(out_scale), float(out_shift), _ptr(out), _ptr(sig), _ptr(nsing), _ptr(ws), ws.numel(), _stream())
+                float(out_scale), float(out_shift), _ptr(out), _ptr(sig), _ptr(nsing), _ptr(ws), ws.numel(), opt,
+                _stream())
     _lib.check(rc, "cmx_ok_mw")
     if return_sigmasq:
         return out, sig, nsing
@@ -424,24 +442,31 @@ def knn3(s_xyz, t_xyz, k: int):
 
 def ok_solve(s_x, s_y, z, idx: torch.Tensor, d2: torch.Tensor, *, variogram_model: str, params,
              geographic: bool = False, exact_values: bool = True, out_scale: float = 1.0, out_shift: float = 0.0,
-             dtype: torch.dtype = torch.float64, return_sigmasq: bool = False):
-    """K4 on an existing neighbour table (``idx``, squared distances ``d2``): one kriging window per row."""
+             dtype: torch.dtype = torch.float64, return_sigmasq: bool = False, solver: str = "auto"):
+    """K4 on an existing neighbour table (``idx``, squared distances ``d2``): one kriging window per row.
+
+    ``solver="auto"``: register Cholesky of the shifted (positive-definite) system with hand-over of
+    ill-conditioned windows to the pivoted kernel; ``"pivoted"``: Gauss-Jordan with partial pivoting for all."""
     lib = _lib.load()
     dev = _require_cuda(idx.device)
+    if solver not in ("auto", "pivoted"):
+        raise ValueError("solver must be 'auto' or 'pivoted'")
     s_x, s_y = _as_f64(s_x, dev), _as_f64(s_y, dev)
     if not isinstance(z, torch.Tensor):
         z = torch.as_tensor(np.ascontiguousarray(z))
-    z = z.to(device=dev, dtype=dtype).contiguous()
+    z = z.to(device=dev, dtype=torch.float64).contiguous()
     m, k = idx.shape
     p = (ctypes.c_double * 3)(*[float(v) for v in list(params) + [0.0] * (3 - len(params))])
     with torch.cuda.device(dev):
         out = torch.empty(m, dtype=dtype, device=dev)
         sig = torch.empty(m, dtype=dtype, device=dev) if return_sigmasq else None
         nsing = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws = _workspace(lib.cmx_ok_solve_workspace_bytes(m), dev) if solver == "auto" else None
         fn = lib.cmx_ok_solve_f64 if dtype == torch.float64 else lib.cmx_ok_solve_f32
         rc = fn(_ptr(s_x), _ptr(s_y), _ptr(z), s_x.numel(), _ptr(idx.contiguous()), _ptr(d2.contiguous()), m,
                 _lib.METRIC_GEOGRAPHIC if geographic else _lib.METRIC_EUCLIDEAN, k, _lib.VARIOGRAM_MODELS[variogram_model],
-                p, int(exact_values), float(out_scale), float(out_shift), _ptr(out), _ptr(sig), _ptr(nsing), _stream())
+                p, int(exact_values), float(out_scale), float(out_shift), _ptr(out), _ptr(sig), _ptr(nsing),
+                _ptr(ws), ws.numel() if ws is not None else 0, _stream())
     _lib.check(rc, "cmx_ok_solve")
     if return_sigmasq:
         return out, sig, nsing

@@ -115,7 +115,8 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
     variogram_model : "linear" | "power" | "gaussian" | "spherical" | "exponential", default "linear"
     pseudo_inv : bool, default False
     n_closest_points / k : int | None  (new) moving-window kriging over the k nearest samples
-    dtype : "float64" | "float32"      (new) dtype of values and result (solves stay float64)
+    dtype : "float64" | "float32"      (new) dtype the result is stored in (values, normalisation and solves stay
+                                       float64, so float32 output differs from float64 by its final rounding only)
     device : torch device              (new)
     """
 
@@ -253,7 +254,7 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
                     gx, gy = gxm.ravel(), gym.ravel()
                 d2, idx = kernels.knn3(unit(x_adj, y_adj), unit(gx, gy), self.n_closest_points)
                 res = kernels.ok_solve(
-                    xs, ys, zs.to(tdtype), idx, d2, variogram_model=self.variogram_model, params=params,
+                    xs, ys, zs, idx, d2, variogram_model=self.variogram_model, params=params,
                     geographic=True, exact_values=True, out_scale=float(v_std), out_shift=float(v_mean), dtype=tdtype,
                     return_sigmasq=self.return_variance,
                 )
@@ -271,7 +272,7 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
                     tx, _ = _anisotropy(xpts, np.full_like(xpts, yc), xc, yc, scaling)
                     _, ty = _anisotropy(np.full_like(ypts, xc), ypts, xc, yc, scaling)
                 res = kernels.ok_moving_window(
-                    xs, ys, zs.to(tdtype), tx, ty, not sparse_target, k=self.n_closest_points,
+                    xs, ys, zs, tx, ty, not sparse_target, k=self.n_closest_points,
                     variogram_model=self.variogram_model, params=params, exact_values=True,
                     out_scale=float(v_std), out_shift=float(v_mean), dtype=tdtype,
                     return_sigmasq=self.return_variance,

@@ -30,7 +30,8 @@
  *    across the ABI.  cmx_strerror() maps codes to text.
  *  - Coordinates are always float64 (neighbour sets must match the reference's
  *    float64 kd-tree bit-exactly); `_f32`/`_f64` names the dtype of sample
- *    values and of the reconstructed field.
+ *    values and of the reconstructed field (IDW) / of the stored field (kriging,
+ *    whose standardised values are always float64).
  *  - Targets: `target_is_grid != 0` -> dense grid, `t_a` is the latitude axis
  *    (n_a rows), `t_b` the longitude axis (n_b columns), target m = i*n_b + j
  *    (row-major, the order of DenseDomain.get_all_spatial_points,
@@ -38,6 +39,9 @@
  *    `t_a[m], t_b[m]`, n_a == n_b == M (SparseDomain, domain.py:738).
  *  - Neighbour order and ties: ascending by (squared distance, sample index),
  *    squared distance = dx*dx + dy*dy in float64 without FMA contraction.
+ *  - No hidden state: everything that changes what a call does is an argument.  Optional behaviour
+ *    (search algorithm, output redirection to peer devices) travels in a `const cmx_options*`
+ *    (NULL = defaults); the library keeps no per-thread or per-process mode.
  */
 #ifndef CLIMATRIX_B200_H
 #define CLIMATRIX_B200_H
@@ -59,6 +63,38 @@ extern "C" {
 #define CMX_ERR_TOO_MANY (-7)       /* more than 2^31-1 samples or targets                */
 
 #define CMX_MAX_K 128
+#define CMX_MAX_PEERS 8
+
+/* ---- per-call options (NULL = all defaults) ----
+ *
+ * search: neighbour-search algorithm of cmx_knn / cmx_idw_* / cmx_ok_mw_*.  All return the same neighbour tables
+ * (exact float64 distances, ties by sample index); they differ only in the work done:
+ *   CMX_SEARCH_BRUTE   K1: every (target, sample) pair is evaluated (north_star's brute-force kernel).
+ *   CMX_SEARCH_BINNED  K1c: samples are counting-sorted into the cells of the seed grid and each target scans
+ *                      only the cells that intersect the disc of its k-th-distance bound - the device counterpart
+ *                      of cKDTree's pruning (reference: reconstruct/idw.py:155-158).  Needs 20 B per sample of
+ *                      the ordinary kNN workspace; if that does not fit, the call uses K1.
+ *   CMX_SEARCH_AUTO    (default) the faster one for the problem: K1c whenever its scratch fits.
+ *
+ * peer_out / n_peers / m_total / m_offset: multi-GPU fused weighting + gather (batched IDW only, n_batch > 1).
+ * With one process per GPU every rank reconstructs a band of target rows and all ranks need the whole field
+ * (reference: one cm.reconstruct call returns the full grid).  Instead of a separate all-gather after the kernel,
+ * the batched weighting kernels store each finished row segment directly into the [n_batch][m_total] output
+ * arrays of n_peers devices (peer-mapped pointers, e.g. torch symmetric memory; NVLink stores through NVSwitch)
+ * at this call's first target m_offset.  The call's own `out` argument is then unused (but must be non-null).
+ * n_peers = 0: plain output.  Synchronising the ranks before the buffers are read is the caller's job.
+ * A redirected call with n_batch == 1 returns CMX_ERR_UNSUPPORTED.
+ */
+#define CMX_SEARCH_AUTO 0
+#define CMX_SEARCH_BRUTE 1
+#define CMX_SEARCH_BINNED 2
+typedef struct cmx_options {
+    int search;
+    int n_peers;
+    void* peer_out[CMX_MAX_PEERS];
+    int64_t m_total;
+    int64_t m_offset;
+} cmx_options;
 
 /* variogram models, pykrige/variogram_models.py (params: see cmx_ok_mw_*) */
 #define CMX_VARIOGRAM_LINEAR 0
@@ -99,7 +135,7 @@ size_t cmx_knn_workspace_bytes_for(int k, int64_t n_samples, int64_t n_a, int64_
 int cmx_knn(const double* s_a, const double* s_b, int64_t n_samples,
             const double* t_a, int64_t n_a, const double* t_b, int64_t n_b, int target_is_grid,
             int k, int32_t* idx_out, double* dist_out,
-            void* workspace, size_t workspace_bytes, void* stream);
+            void* workspace, size_t workspace_bytes, const cmx_options* options, void* stream);
 
 /* ---- inverse distance weighting ---- */
 
@@ -117,13 +153,13 @@ int cmx_idw_f64(const double* s_lat, const double* s_lon, int64_t n_samples,
                 const double* t_lat, int64_t n_lat, const double* t_lon, int64_t n_lon, int target_is_grid,
                 int k, int k_min, double power,
                 double* out, int32_t* idx_out, double* dist_out,
-                void* workspace, size_t workspace_bytes, void* stream);
+                void* workspace, size_t workspace_bytes, const cmx_options* options, void* stream);
 int cmx_idw_f32(const double* s_lat, const double* s_lon, int64_t n_samples,
                 const float* vals, int64_t n_batch, int vals_layout,
                 const double* t_lat, int64_t n_lat, const double* t_lon, int64_t n_lon, int target_is_grid,
                 int k, int k_min, double power,
                 float* out, int32_t* idx_out, double* dist_out,
-                void* workspace, size_t workspace_bytes, void* stream);
+                void* workspace, size_t workspace_bytes, const cmx_options* options, void* stream);
 
 /*
  * Re-apply idw.py:163-180 to a stored neighbour table with other (k_use <= k_table,
@@ -134,10 +170,12 @@ int cmx_idw_f32(const double* s_lat, const double* s_lon, int64_t n_samples,
  */
 int cmx_idw_apply_f64(const int32_t* idx, const double* dist, int64_t n_targets, int k_table,
                       const double* vals, int64_t n_samples, int64_t n_batch, int vals_layout,
-                      int k_use, int k_min, double power, double* out, int32_t* flag_scratch, void* stream);
+                      int k_use, int k_min, double power, double* out, int32_t* flag_scratch,
+                      const cmx_options* options, void* stream);
 int cmx_idw_apply_f32(const int32_t* idx, const double* dist, int64_t n_targets, int k_table,
                       const float* vals, int64_t n_samples, int64_t n_batch, int vals_layout,
-                      int k_use, int k_min, double power, float* out, int32_t* flag_scratch, void* stream);
+                      int k_use, int k_min, double power, float* out, int32_t* flag_scratch,
+                      const cmx_options* options, void* stream);
 
 /* ---- empirical variogram (pykrige core._initialize_variogram_model) ---- */
 
@@ -160,13 +198,17 @@ int cmx_variogram_bins(const double* x, const double* y, const double* z, int64_
  * anisotropy-adjusted; CMX_METRIC_GEOGRAPHIC: x = lon, y = lat in degrees, neighbours
  * by 3-D chord, distances great-circle degrees), assemble the (k+1)x(k+1) system
  * A = [[-gamma(D), 1], [1^T, 0]] (zero diagonal), b = [-gamma(d); 1] with entries
- * forced to 0 where d <= 1e-10 (exact_values), solve by LU with partial pivoting in
- * float64, z = sum_i x_i Z_i, sigmasq = -x.b.   pykrige ok.py
- * _exec_loop_moving_window, reached from kriging.py:236-241.
+ * forced to 0 where d <= 1e-10 (exact_values), solve in float64,
+ * z = sum_i x_i Z_i, sigmasq = -x.b.   pykrige ok.py _exec_loop_moving_window, reached from
+ * kriging.py:236-241 (which solves by LU with partial pivoting).
+ * Solver: k <= 64 -> Cholesky of the equivalent positive-definite system A + c0 11^T in registers
+ * (DESIGN.md K4); windows whose pivots fall below 1e-9 c0 (cond > ~1e9), k > 64 and k == 1 -> Gauss-Jordan
+ * with partial pivoting, which also defines the singular case.
  * params: linear [slope, nugget, -]; power [scale, exponent, nugget];
  *         gaussian/spherical/exponential [psill, range, nugget].
- * out[m] = z * out_scale + out_shift: the de-standardisation of kriging.py:245 fused into
- * the store (pass 1, 0 for plain pykrige output).
+ * z [N] is float64 in both variants (kriging.py:207-214 standardises the values in float64); `_f32`/`_f64`
+ * names the dtype the field and the variance are STORED in.  out[m] = z * out_scale + out_shift: the
+ * de-standardisation of kriging.py:245 fused into the store (pass 1, 0 for plain pykrige output).
  * out [M] (required), sigmasq_out [M] (may be NULL); NaN + *n_singular++ where the
  * local system is singular (duplicate neighbours; the reference raises LinAlgError).
  */
@@ -175,13 +217,13 @@ int cmx_ok_mw_f64(const double* s_x, const double* s_y, const double* z, int64_t
                   int metric, int k, int variogram_model, const double params[3], int exact_values,
                   double out_scale, double out_shift,
                   double* out, double* sigmasq_out, int32_t* n_singular,
-                  void* workspace, size_t workspace_bytes, void* stream);
-int cmx_ok_mw_f32(const double* s_x, const double* s_y, const float* z, int64_t n_samples,
+                  void* workspace, size_t workspace_bytes, const cmx_options* options, void* stream);
+int cmx_ok_mw_f32(const double* s_x, const double* s_y, const double* z, int64_t n_samples,
                   const double* t_x, int64_t n_x, const double* t_y, int64_t n_y, int target_is_grid,
                   int metric, int k, int variogram_model, const double params[3], int exact_values,
                   double out_scale, double out_shift,
                   float* out, float* sigmasq_out, int32_t* n_singular,
-                  void* workspace, size_t workspace_bytes, void* stream);
+                  void* workspace, size_t workspace_bytes, const cmx_options* options, void* stream);
 /*
  * Geographic mode (pykrige coordinates_type="geographic"), in two calls:
  *  cmx_knn3       exact 3-D k-NN between unit vectors (cKDTree on (cos lon cos lat, sin lon cos lat,
@@ -191,61 +233,34 @@ int cmx_ok_mw_f32(const double* s_x, const double* s_y, const float* z, int64_t 
  *                 chords (converted by 180 - 360/pi acos(chord/2)), s_x = lon, s_y = lat in degrees and
  *                 the window matrix uses the great-circle (Vincenty atan2) distance;
  *                 CMX_METRIC_EUCLIDEAN: d2 holds squared Euclidean distances in the (s_x, s_y) frame.
+ *                 workspace: cmx_ok_solve_workspace_bytes(n_targets) bytes of scratch for the list of windows
+ *                 the Cholesky solver hands to the pivoted one; NULL (or too small) -> every window is solved
+ *                 by the pivoted Gauss-Jordan kernel (same results within rounding; ~5x slower at k = 64).
  */
 int cmx_knn3(const double* s_x, const double* s_y, const double* s_z, int64_t n_samples,
              const double* t_x, const double* t_y, const double* t_z, int64_t n_targets,
              int k, int32_t* idx_out, double* d2_out, void* stream);
+size_t cmx_ok_solve_workspace_bytes(int64_t n_targets);
 int cmx_ok_solve_f64(const double* s_x, const double* s_y, const double* z, int64_t n_samples,
                      const int32_t* idx, const double* d2, int64_t n_targets, int metric, int k,
                      int variogram_model, const double params[3], int exact_values,
                      double out_scale, double out_shift,
-                     double* out, double* sigmasq_out, int32_t* n_singular, void* stream);
-int cmx_ok_solve_f32(const double* s_x, const double* s_y, const float* z, int64_t n_samples,
+                     double* out, double* sigmasq_out, int32_t* n_singular,
+                     void* workspace, size_t workspace_bytes, void* stream);
+int cmx_ok_solve_f32(const double* s_x, const double* s_y, const double* z, int64_t n_samples,
                      const int32_t* idx, const double* d2, int64_t n_targets, int metric, int k,
                      int variogram_model, const double params[3], int exact_values,
                      double out_scale, double out_shift,
-                     float* out, float* sigmasq_out, int32_t* n_singular, void* stream);
+                     float* out, float* sigmasq_out, int32_t* n_singular,
+                     void* workspace, size_t workspace_bytes, void* stream);
 
-/* total scratch for cmx_ok_mw_* (includes the kNN scratch) */
+/* total scratch for cmx_ok_mw_* (includes the kNN scratch and cmx_ok_solve_workspace_bytes) */
 size_t cmx_ok_workspace_bytes(int k, int64_t n_targets);
 
-/* Work decomposition cmx_knn (brute force) would use for these sizes on the current device: targets per thread
+/* Work decomposition cmx_knn (CMX_SEARCH_BRUTE) would use for these sizes on the current device: targets per thread
  * (tile height in rows: 16, 8, 2 or 1) and the number of sample segments (1 = no split).  Host-only query, for
  * benchmarks and tests of the planner (DESIGN.md K1 "Planner").  Returns CMX_OK or CMX_ERR_BAD_ARG. */
 int cmx_knn_plan(int64_t n_samples, int64_t n_a, int64_t n_b, int grid, int* tile_rows, int* sample_segments);
-
-/* ---- neighbour-search algorithm ----
- *
- * Every entry point that searches planar neighbours (cmx_knn, cmx_idw_*, cmx_ok_mw_*) uses the algorithm
- * selected here for the calling thread.  Both return the same neighbour tables (exact float64 distances,
- * ties by sample index); they differ only in the work done:
- *   CMX_SEARCH_BRUTE  (default) K1: every (target, sample) pair is evaluated (north_star's brute-force kernel).
- *   CMX_SEARCH_BINNED K1c: samples are counting-sorted into the cells of the seed grid and each target scans
- *                     only the cells that intersect the disc of its k-th-distance bound - the device counterpart
- *                     of cKDTree's pruning (reference: reconstruct/idw.py:155-158).  Needs 20 B per sample of
- *                     the ordinary kNN workspace; if that does not fit, the call uses K1.
- * cmx_set_search returns the previous setting, or CMX_ERR_BAD_ARG.
- */
-#define CMX_SEARCH_BRUTE 0
-#define CMX_SEARCH_BINNED 1
-int cmx_set_search(int algorithm);
-int cmx_get_search(void);
-
-/* ---- multi-GPU: fused weighting + gather over peer memory ----
- *
- * With one process per GPU every rank reconstructs a band of target rows and all ranks need the whole field
- * (reference: one cm.reconstruct call returns the full grid).  Instead of a separate all-gather after the kernel,
- * the batched weighting kernels can store each finished row segment directly into the output buffers of ALL ranks
- * (NVLink peer stores through NVSwitch): call cmx_set_output_peers with the n_peers device pointers of the
- * [n_batch][m_total] output arrays (peer-mapped, e.g. torch symmetric memory), the total number of targets m_total
- * and this rank's first target m_offset.  The setting applies to the NEXT cmx_idw_f64/_f32 or cmx_idw_apply_*
- * call of this thread with n_batch > 1 and is cleared by it; that call's own `out` argument is then unused (but
- * must be non-null).  n_peers = 0 clears.  Synchronising the ranks before the buffers are read is the caller's
- * job (e.g. a symmetric-memory barrier).  Errors: CMX_ERR_BAD_ARG; a redirected call with n_batch == 1 returns
- * CMX_ERR_UNSUPPORTED.
- */
-#define CMX_MAX_PEERS 8
-int cmx_set_output_peers(void* const* peer_out, int n_peers, int64_t m_total, int64_t m_offset);
 
 /* ---- host transfer helper ----
  * Asynchronous strided device -> host copy (cudaMemcpy2DAsync): `rows` rows of `width_bytes` bytes from a device
@@ -264,8 +279,9 @@ void cmx_reset_launch_count(void);
 /*
  * Optional per-kernel device timing (bench.py's roofline): when enabled, the library brackets
  * its two hot kernels with CUDA events on the launching stream.
- *   kind 0 = K1 neighbour search (knn_kernel), kind 1 = K2 batched IDW apply, kind 2 = K4 kriging solve,
- *   kind 3 = K1c cell-binned neighbour search (scatter + knn_binned_kernel).
+ *   kind 0 = K1 neighbour search (knn_kernel), kind 1 = K2 batched IDW apply, kind 2 = K4 kriging solve
+ *   (Cholesky kernel + the pivoted kernel on its hand-over list), kind 3 = K1c cell-binned neighbour search
+ *   (scatter + knn_binned_kernel).
  * cmx_timing_read synchronises on the recorded events and returns the accumulated
  * milliseconds and the number of launches since the last cmx_timing_reset.
  */

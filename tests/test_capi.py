@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 
 def test_version_and_error_strings(lib):
-    assert lib.cmx_version() >= 100
+    assert lib.cmx_version() >= 200
     assert lib.cmx_strerror(0) == b"ok"
     assert b"exceeds the number of samples" in lib.cmx_strerror(_lib.ERR_K_GT_N)
     assert lib.cmx_strerror(-99) == b"unknown error"
@@ -50,20 +50,24 @@ def test_argument_validation_returns_codes_without_a_device(lib):
     null = ctypes.c_void_p(None)
     one = ctypes.c_void_p(16)  # never dereferenced: validation fails first
     # null pointers
-    assert lib.cmx_knn(null, null, 10, null, 1, null, 1, 1, 3, null, null, null, 0, null) == _lib.ERR_BAD_ARG
+    assert lib.cmx_knn(null, null, 10, null, 1, null, 1, 1, 3, null, null, null, 0, None, null) == _lib.ERR_BAD_ARG
     # k > n
-    assert lib.cmx_knn(one, one, 2, one, 1, one, 1, 1, 3, one, null, one, 1 << 40, null) == _lib.ERR_K_GT_N
+    assert lib.cmx_knn(one, one, 2, one, 1, one, 1, 1, 3, one, null, one, 1 << 40, None, null) == _lib.ERR_K_GT_N
     # k above CMX_MAX_K
-    assert lib.cmx_knn(one, one, 1000, one, 1, one, 1, 1, 129, one, null, one, 1 << 40, null) == _lib.ERR_K_TOO_LARGE
+    assert lib.cmx_knn(one, one, 1000, one, 1, one, 1, 1, 129, one, null, one, 1 << 40, None, null) == _lib.ERR_K_TOO_LARGE
     # workspace too small
-    assert lib.cmx_knn(one, one, 1000, one, 4, one, 4, 1, 8, one, null, one, 16, null) == _lib.ERR_WORKSPACE
+    assert lib.cmx_knn(one, one, 1000, one, 4, one, 4, 1, 8, one, null, one, 16, None, null) == _lib.ERR_WORKSPACE
     # sparse targets need matching lengths
-    assert lib.cmx_knn(one, one, 1000, one, 4, one, 5, 0, 8, one, null, one, 1 << 40, null) == _lib.ERR_BAD_ARG
+    assert lib.cmx_knn(one, one, 1000, one, 4, one, 5, 0, 8, one, null, one, 1 << 40, None, null) == _lib.ERR_BAD_ARG
     # variogram: too many lags / unknown metric
     assert lib.cmx_variogram_bins(one, one, one, 10, 0, 65, one, one, one, one, null) == _lib.ERR_UNSUPPORTED
     assert lib.cmx_variogram_minmax(one, one, 10, 7, one, null) == _lib.ERR_UNSUPPORTED
     p = (ctypes.c_double * 3)(1.0, 1.0, 0.0)
-    assert lib.cmx_ok_mw_f64(one, one, one, 10, one, 2, one, 2, 1, 0, 4, 9, p, 1, 1.0, 0.0, one, null, null, one, 1 << 40, null) == _lib.ERR_UNSUPPORTED
+    assert lib.cmx_ok_mw_f64(one, one, one, 10, one, 2, one, 2, 1, 0, 4, 9, p, 1, 1.0, 0.0, one, null, null, one, 1 << 40,
+                             None, null) == _lib.ERR_UNSUPPORTED
+    assert lib.cmx_ok_solve_f64(one, one, one, 10, one, one, 5, 0, 200, 0, p, 1, 1.0, 0.0, one, null, null, null, 0,
+                                null) == _lib.ERR_K_TOO_LARGE
+    assert lib.cmx_ok_solve_workspace_bytes(1000) >= 4000
 
 
 def test_check_maps_codes_to_python_exceptions():
@@ -78,39 +82,50 @@ def test_check_maps_codes_to_python_exceptions():
     _lib.check(0)
 
 
-def test_search_selection_is_host_state():
-    lib = _lib.load()
-    assert lib.cmx_get_search() == 0  # brute force is the default
-    assert lib.cmx_set_search(1) == 0
-    assert lib.cmx_get_search() == 1
-    assert lib.cmx_set_search(7) == _lib.ERR_BAD_ARG
-    assert lib.cmx_get_search() == 1
-    assert lib.cmx_set_search(0) == 1
+def test_options_are_explicit_arguments_and_validated_before_any_device_work(lib):
+    """cmx_options replaces the per-thread cmx_set_search / cmx_set_output_peers of ABI 0.1: no hidden state."""
+    for gone in ("cmx_set_search", "cmx_get_search", "cmx_set_output_peers"):
+        assert not hasattr(lib, gone)
+    null, one = ctypes.c_void_p(None), ctypes.c_void_p(16)
+
+    def knn_with(opt):  # k > n would be reported next: proves the options were accepted
+        return lib.cmx_knn(one, one, 2, one, 1, one, 1, 1, 3, one, null, one, 1 << 40, ctypes.byref(opt), null)
+
+    opt = _lib.Options()
+    for search in (_lib.SEARCH_AUTO, _lib.SEARCH_BRUTE, _lib.SEARCH_BINNED):
+        opt.search = search
+        assert knn_with(opt) == _lib.ERR_K_GT_N
+    opt.search = 7
+    assert knn_with(opt) == _lib.ERR_BAD_ARG
+    opt.search = _lib.SEARCH_AUTO
+    opt.n_peers = 2  # cmx_knn has no redirectable output
+    opt.peer_out[0] = opt.peer_out[1] = 16
+    opt.m_total, opt.m_offset = 10, 0
+    assert knn_with(opt) == _lib.ERR_UNSUPPORTED
+
+    def idw_with(opt):  # batched call; n_batch < 1 would be BAD_ARG, so use k_min = 0 as the next error
+        return lib.cmx_idw_f64(one, one, 100, one, 4, 1, one, 2, one, 2, 1, 3, 0, 2.0, one, null, null, one, 1 << 40,
+                               ctypes.byref(opt), null)
+
+    opt.n_peers = 9
+    assert idw_with(opt) == _lib.ERR_BAD_ARG
+    opt.n_peers = 2
+    opt.m_offset = 11  # beyond m_total
+    assert idw_with(opt) == _lib.ERR_BAD_ARG
+    opt.m_offset = 5
+    opt.peer_out[1] = None
+    assert idw_with(opt) == _lib.ERR_BAD_ARG
+    opt.peer_out[1] = 16
+    assert idw_with(opt) == _lib.ERR_BAD_ARG  # options fine -> the k_min = 0 argument error
+
     import climatrix_b200 as cm
 
-    assert cm.get_search() == "brute"
-    assert cm.set_search("binned") == "brute"
+    assert cm.get_search() == "auto"
+    assert cm.set_search("binned") == "auto"
     assert cm.set_search("brute") == "binned"
-    import pytest
-
+    assert cm.set_search("auto") == "brute"
     with pytest.raises(ValueError):
         cm.set_search("kd-tree")
-
-
-def test_output_peers_argument_checks():
-    import ctypes
-
-    lib = _lib.load()
-    one = ctypes.c_void_p(8)
-    arr = (ctypes.c_void_p * 2)(one, one)
-    assert lib.cmx_set_output_peers(None, 0, 0, 0) == 0  # clears
-    assert lib.cmx_set_output_peers(None, 2, 10, 0) == _lib.ERR_BAD_ARG
-    assert lib.cmx_set_output_peers(arr, 9, 10, 0) == _lib.ERR_BAD_ARG
-    assert lib.cmx_set_output_peers(arr, 2, 10, 11) == _lib.ERR_BAD_ARG
-    bad = (ctypes.c_void_p * 2)(one, None)
-    assert lib.cmx_set_output_peers(bad, 2, 10, 0) == _lib.ERR_BAD_ARG
-    assert lib.cmx_set_output_peers(arr, 2, 10, 5) == 0
-    assert lib.cmx_set_output_peers(None, 0, 0, 0) == 0
 
 
 def test_planner_choices_for_bands_of_a_big_job():

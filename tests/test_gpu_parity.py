@@ -137,7 +137,8 @@ def test_knn_unaligned_sample_pointers_take_the_plain_load_path():
     dist = torch.empty((T.count, 12), dtype=torch.float64, device=DEV)
     ws = torch.empty(lib.cmx_knn_workspace_bytes(12), dtype=torch.uint8, device=DEV)
     rc = lib.cmx_knn(s_la.data_ptr(), s_lo.data_ptr(), 5000, T.lat.data_ptr(), 33, T.lon.data_ptr(), 65, 1, 12,
-                     idx.data_ptr(), dist.data_ptr(), ws.data_ptr(), ws.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                     idx.data_ptr(), dist.data_ptr(), ws.data_ptr(), ws.numel(), K._options(),
+                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert rc == 0
     d0, i0 = knn_ckdtree(sparse_points(la[1:], lo[1:]), dense_points(tl, to), 12)
     np.testing.assert_array_equal(idx.cpu().numpy(), i0)
@@ -422,8 +423,8 @@ def test_ok_reconstructor_moving_window_matches_golden(name, dtype):
     # the fitted variogram parameters come from the GPU variogram + the same SciPy fit
     np.testing.assert_allclose(rec.variogram_model_parameters, g["variogram_parameters"], rtol=1e-6, atol=1e-9)
     scale = np.max(np.abs(g["expected"]))
-    tol = OK_RTOL if dtype == "float64" else 5e-4  # float32 stores values/results at 6e-8 relative
-    assert np.max(np.abs(got - g["expected"])) <= tol * scale
+    # north_star: 1e-4 in fp32 and fp64 - values, normalisation and solves stay float64, only the store rounds
+    assert np.max(np.abs(got - g["expected"])) <= OK_RTOL * scale
 
 
 @pytest.mark.parametrize("name", [n for n in golden_names("ok_global_") if "gaussian" not in n and "pinv" not in n])
@@ -534,7 +535,7 @@ def test_idw_batch_peer_output_redirection(n_batch, k):
     for b in bufs:
         assert torch.equal(b[:, off:off + m], plain)
         assert bool((b[:, :off] == -7.0).all()) and bool((b[:, off + m:] == -7.0).all())
-    # the redirection is consumed by one call: the next plain call is unaffected
+    # the redirection is an argument of that one call (cmx_options): a plain call is unaffected
     assert torch.equal(K.idw(la, lo, vals, tg, k=k, layout="sample_major"), plain)
     with pytest.raises(ValueError):
         K.idw(la, lo, vals[:, 0], tg, k=k, peer_out=([bufs[0].data_ptr()], m_total, off))
