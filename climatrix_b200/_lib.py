@@ -43,8 +43,8 @@ SIGNATURES = {
     "cmx_idw_f32": (c_int, [_P, _P, c_i64, _P, c_i64, c_int, _P, c_i64, _P, c_i64, c_int, c_int, c_int, c_double, _P, _P, _P, _P, c_size_t, _OPT, _P]),
     "cmx_idw_apply_f64": (c_int, [_P, _P, c_i64, c_int, _P, c_i64, c_i64, c_int, c_int, c_int, c_double, _P, _P, _OPT, _P]),
     "cmx_idw_apply_f32": (c_int, [_P, _P, c_i64, c_int, _P, c_i64, c_i64, c_int, c_int, c_int, c_double, _P, _P, _OPT, _P]),
-    "cmx_variogram_minmax": (c_int, [_P, _P, c_i64, c_int, _P, _P]),
-    "cmx_variogram_bins": (c_int, [_P, _P, _P, c_i64, c_int, c_int, _P, _P, _P, _P, _P]),
+    "cmx_variogram_minmax": (c_int, [_P, _P, c_i64, c_int, c_int, c_int, _P, _P]),
+    "cmx_variogram_bins": (c_int, [_P, _P, _P, c_i64, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "cmx_ok_workspace_bytes": (c_size_t, [c_int, c_i64]),
     "cmx_ok_mw_f64": (c_int, [_P, _P, _P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, c_int, c_int, ctypes.POINTER(c_double), c_int, c_double, c_double, _P, _P, _P, _P, c_size_t, _OPT, _P]),
     "cmx_ok_mw_f32": (c_int, [_P, _P, _P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, c_int, c_int, ctypes.POINTER(c_double), c_int, c_double, c_double, _P, _P, _P, _P, c_size_t, _OPT, _P]),
@@ -52,6 +52,7 @@ SIGNATURES = {
     "cmx_timing_reset": (None, []),
     "cmx_timing_read": (c_int, [c_int, ctypes.POINTER(c_double), ctypes.POINTER(c_i64)]),
     "cmx_fp32_peak_tflops": (c_double, []),
+    "cmx_fp64_peak_tflops": (c_double, []),
     "cmx_knn3": (c_int, [_P, _P, _P, c_i64, _P, _P, _P, c_i64, c_int, _P, _P, _P]),
     "cmx_ok_solve_workspace_bytes": (c_size_t, [c_i64]),
     "cmx_ok_solve_f64": (c_int, [_P, _P, _P, c_i64, _P, _P, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_double), c_int, c_double, c_double, _P, _P, _P, _P, c_size_t, _P]),

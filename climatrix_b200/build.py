@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.environ.get("CMX_LIB") or os.path.join(LIB_DIR, "libclimatrix_b200.so")  # CMX_LIB: tuning variants
 SOURCES = ["capi.cu", "knn.cu", "knn3.cu", "idw.cu", "variogram.cu", "kriging.cu"]
-HEADERS = ["common.cuh", "rerank.cuh", os.path.join("..", "..", "include", "climatrix_b200.h")]
+HEADERS = ["common.cuh", "rerank.cuh", "ok_chol.cuh", os.path.join("..", "..", "include", "climatrix_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -50,17 +50,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIB_DIR, exist_ok=True)
     obj_dir = os.path.join(HERE, "..", "build", "obj")
     os.makedirs(obj_dir, exist_ok=True)
-    objs = []
-    log = []
-    for src in SOURCES:
+    from concurrent.futures import ThreadPoolExecutor
+
+    def compile_one(src):
         obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
         cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        log.append(r.stderr)
-        if r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
-            raise RuntimeError(f"nvcc failed on {src}")
-        objs.append(obj)
+        return src, obj, subprocess.run(cmd, capture_output=True, text=True)
+
+    objs = []
+    log = []
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:  # one nvcc per source file
+        for src, obj, r in pool.map(compile_one, SOURCES):
+            log.append(r.stderr)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError(f"nvcc failed on {src}")
+            objs.append(obj)
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

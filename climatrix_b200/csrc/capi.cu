@@ -180,8 +180,46 @@ __global__ void ffma_peak_kernel(float* out, float a, float b, int iters) {
     for (int i = 0; i < 16; ++i) s += acc[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+__global__ void dfma_peak_kernel(double* out, double a, double b, int iters) {
+    double acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = threadIdx.x * 0.001 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fma(acc[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
 }  // namespace
 }  // namespace cmx
+
+double cmx_fp64_peak_tflops(void) {
+    const int threads = 256, iters = 4096;
+    const int blocks = cmx::sm_count() * 4;  // 32 warps per SM x 8 independent chains
+    double* out = nullptr;
+    if (cudaMalloc(&out, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = -1.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        cmx::dfma_peak_kernel<<<blocks, threads>>>(out, 1.0000001, 0.5, iters);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = (double)blocks * threads * iters * 8 * 2 / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;  // first launch warms up
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return best;
+}
 
 double cmx_fp32_peak_tflops(void) {
     const int threads = 256, iters = 8192;

@@ -47,12 +47,14 @@ __global__ void minmax_init_kernel(double* minmax) {
 template <int METRIC>
 __global__ void __launch_bounds__(VT) variogram_minmax_kernel(const double* __restrict__ x,
                                                               const double* __restrict__ y, long long n,
-                                                              long long n_blocks, double* minmax) {
+                                                              long long n_blocks, long long part, long long n_parts,
+                                                              double* minmax) {
     __shared__ double sx[VT], sy[VT];
     __shared__ double red[2 * VT / 32];
     const int tid = threadIdx.x;
     double lo = __longlong_as_double(0x7ff0000000000000LL), hi = -lo;
-    for (long long b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+    // this call's share of the lower-triangle blocks: b = part (mod n_parts)
+    for (long long b = part + n_parts * blockIdx.x; b < n_blocks; b += n_parts * gridDim.x) {
         int bi, bj;
         tile_of_block(b, bi, bj);
         const long long i = (long long)bi * VT + tid;
@@ -99,8 +101,8 @@ template <int METRIC>
 __global__ void __launch_bounds__(VT) variogram_bins_kernel(const double* __restrict__ x,
                                                             const double* __restrict__ y,
                                                             const double* __restrict__ z, long long n,
-                                                            long long n_blocks, int nlags,
-                                                            const double* __restrict__ edges, double* sum_d,
+                                                            long long n_blocks, long long part, long long n_parts,
+                                                            int nlags, const double* __restrict__ edges, double* sum_d,
                                                             double* sum_g, unsigned long long* count) {
     __shared__ double sx[VT], sy[VT], sz[VT];
     __shared__ double s_edges[MAX_LAGS + 1];
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(VT) variogram_bins_kernel(const double* __rest
     const double e0 = s_edges[0];
     const double inv_dd = nlags > 0 && s_edges[1] > e0 ? 1.0 / (s_edges[1] - e0) : 0.0;
 
-    for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+    for (long long blk = part + n_parts * blockIdx.x; blk < n_blocks; blk += n_parts * gridDim.x) {
         int bi, bj;
         tile_of_block(blk, bi, bj);
         const long long i = (long long)bi * VT + tid;
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(VT) variogram_bins_kernel(const double* __rest
                     acc_c[b] += 1u;
                 }
             }
-            // keep 32-bit per-thread counters safe on very long sweeps
+            // (32-bit per-thread counters: a thread sees at most n_blocks / gridDim.x * 256 < 2^32 pairs for n < 2^31)
         }
     }
     // block reduction per bin, then one atomic per bin and CTA
@@ -184,41 +186,46 @@ __global__ void __launch_bounds__(VT) variogram_bins_kernel(const double* __rest
 
 extern "C" {
 
-int cmx_variogram_minmax(const double* x, const double* y, int64_t n, int metric, double* minmax, void* stream_) {
+int cmx_variogram_minmax(const double* x, const double* y, int64_t n, int metric, int part, int n_parts,
+                         double* minmax, void* stream_) {
     using namespace cmx;
-    if (!x || !y || !minmax || n < 2) return CMX_ERR_BAD_ARG;
+    if (!x || !y || !minmax || n < 2 || n_parts < 1 || part < 0 || part >= n_parts) return CMX_ERR_BAD_ARG;
     if (metric != CMX_METRIC_EUCLIDEAN && metric != CMX_METRIC_GEOGRAPHIC) return CMX_ERR_UNSUPPORTED;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const long long nb = (n + VT - 1) / VT;
     const long long n_blocks = nb * (nb + 1) / 2;
-    const int grid = (int)(n_blocks < (long long)sm_count() * 8 ? n_blocks : (long long)sm_count() * 8);
+    const long long mine = (n_blocks - part + n_parts - 1) / n_parts;  // blocks of this part (may be 0)
+    const int grid = (int)(mine < (long long)sm_count() * 8 ? (mine > 0 ? mine : 1) : (long long)sm_count() * 8);
     minmax_init_kernel<<<1, 1, 0, stream>>>(minmax);
     note_launch();
     if (metric == CMX_METRIC_EUCLIDEAN)
-        variogram_minmax_kernel<CMX_METRIC_EUCLIDEAN><<<grid, VT, 0, stream>>>(x, y, n, n_blocks, minmax);
+        variogram_minmax_kernel<CMX_METRIC_EUCLIDEAN><<<grid, VT, 0, stream>>>(x, y, n, n_blocks, part, n_parts, minmax);
     else
-        variogram_minmax_kernel<CMX_METRIC_GEOGRAPHIC><<<grid, VT, 0, stream>>>(x, y, n, n_blocks, minmax);
+        variogram_minmax_kernel<CMX_METRIC_GEOGRAPHIC><<<grid, VT, 0, stream>>>(x, y, n, n_blocks, part, n_parts, minmax);
     note_launch();
     return check_launch();
 }
 
-int cmx_variogram_bins(const double* x, const double* y, const double* z, int64_t n, int metric, int nlags,
-                       const double* edges, double* sum_d, double* sum_g, unsigned long long* count,
-                       void* stream_) {
+int cmx_variogram_bins(const double* x, const double* y, const double* z, int64_t n, int metric, int part,
+                       int n_parts, int nlags, const double* edges, double* sum_d, double* sum_g,
+                       unsigned long long* count, void* stream_) {
     using namespace cmx;
     if (!x || !y || !z || !edges || !sum_d || !sum_g || !count || n < 2 || nlags < 1) return CMX_ERR_BAD_ARG;
+    if (n_parts < 1 || part < 0 || part >= n_parts) return CMX_ERR_BAD_ARG;
     if (nlags > MAX_LAGS) return CMX_ERR_UNSUPPORTED;
     if (metric != CMX_METRIC_EUCLIDEAN && metric != CMX_METRIC_GEOGRAPHIC) return CMX_ERR_UNSUPPORTED;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const long long nb = (n + VT - 1) / VT;
     const long long n_blocks = nb * (nb + 1) / 2;
-    const int grid = (int)(n_blocks < (long long)sm_count() * 8 ? n_blocks : (long long)sm_count() * 8);
+    const long long mine = (n_blocks - part + n_parts - 1) / n_parts;
+    if (mine <= 0) return CMX_OK;
+    const int grid = (int)(mine < (long long)sm_count() * 8 ? mine : (long long)sm_count() * 8);
     if (metric == CMX_METRIC_EUCLIDEAN)
         variogram_bins_kernel<CMX_METRIC_EUCLIDEAN>
-            <<<grid, VT, 0, stream>>>(x, y, z, n, n_blocks, nlags, edges, sum_d, sum_g, count);
+            <<<grid, VT, 0, stream>>>(x, y, z, n, n_blocks, part, n_parts, nlags, edges, sum_d, sum_g, count);
     else
         variogram_bins_kernel<CMX_METRIC_GEOGRAPHIC>
-            <<<grid, VT, 0, stream>>>(x, y, z, n, n_blocks, nlags, edges, sum_d, sum_g, count);
+            <<<grid, VT, 0, stream>>>(x, y, z, n, n_blocks, part, n_parts, nlags, edges, sum_d, sum_g, count);
     note_launch();
     return check_launch();
 }

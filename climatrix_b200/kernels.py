@@ -185,6 +185,11 @@ def fp32_peak_tflops() -> float:
     return float(_lib.load().cmx_fp32_peak_tflops())
 
 
+def fp64_peak_tflops() -> float:
+    _require_cuda()
+    return float(_lib.load().cmx_fp64_peak_tflops())
+
+
 def _knn_ws_bytes(lib, k: int, n: int, targets: "Targets") -> int:
     kk = max(1, min(int(k), _lib.MAX_K))
     return int(lib.cmx_knn_workspace_bytes_for(kk, int(n), targets.lat.numel(), targets.lon.numel(), int(targets.grid)))
@@ -347,11 +352,14 @@ def idw_apply(idx: torch.Tensor, dist: torch.Tensor, values, *, k: int | None = 
     return out
 
 
-def empirical_variogram(x, y, z, nlags: int, *, geographic: bool = False):
+def empirical_variogram(x, y, z, nlags: int, *, geographic: bool = False, group=None):
     """pykrige ``_initialize_variogram_model`` binning on the device.
 
     Returns ``(lags, semivariance)`` NumPy arrays with empty bins dropped, plus the
     raw dict (dmin, dmax, edges, sum_d, sum_g, count).  SURVEY.md Appendix A.1 step 3.
+
+    ``group``: a ``torch.distributed`` process group (one rank per GPU, samples replicated) - every rank sweeps
+    its share of the pair blocks and the 2 + 3 nlags partial results are all-reduced.
     """
     lib = _lib.load()
     dev = _require_cuda(x.device if isinstance(x, torch.Tensor) else None)
@@ -359,9 +367,24 @@ def empirical_variogram(x, y, z, nlags: int, *, geographic: bool = False):
     n = x.numel()
     metric = _lib.METRIC_GEOGRAPHIC if geographic else _lib.METRIC_EUCLIDEAN
     nlags = int(nlags)
+    if nlags > 64:
+        raise NotImplementedError("nlags above 64 is not supported by the variogram kernel (climatrix's range is 4..20)")
+    part, n_parts, dist = 0, 1, None
+    if group is not None:
+        import torch.distributed as dist
+
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            part, n_parts = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            dist = None
     with torch.cuda.device(dev):
         mm = torch.empty(2, dtype=torch.float64, device=dev)
-        _lib.check(lib.cmx_variogram_minmax(_ptr(x), _ptr(y), n, metric, _ptr(mm), _stream()), "cmx_variogram_minmax")
+        _lib.check(lib.cmx_variogram_minmax(_ptr(x), _ptr(y), n, metric, part, n_parts, _ptr(mm), _stream()),
+                   "cmx_variogram_minmax")
+        if dist is not None:
+            mm[0].neg_()  # one MAX all-reduce for (-min, max)
+            dist.all_reduce(mm, op=dist.ReduceOp.MAX, group=group)
+            mm[0].neg_()
         dmin, dmax = (float(v) for v in mm.cpu())
         # bin edges exactly as pykrige builds them (python floats): dmin + n*dd, last edge dmax + 0.001
         dd = (dmax - dmin) / nlags
@@ -369,8 +392,11 @@ def empirical_variogram(x, y, z, nlags: int, *, geographic: bool = False):
         edges_t = torch.tensor(edges, dtype=torch.float64, device=dev)
         sums = torch.zeros((2, nlags), dtype=torch.float64, device=dev)
         count = torch.zeros(nlags, dtype=torch.int64, device=dev)
-        _lib.check(lib.cmx_variogram_bins(_ptr(x), _ptr(y), _ptr(z), n, metric, nlags, _ptr(edges_t), _ptr(sums[0]),
-                                          _ptr(sums[1]), _ptr(count), _stream()), "cmx_variogram_bins")
+        _lib.check(lib.cmx_variogram_bins(_ptr(x), _ptr(y), _ptr(z), n, metric, part, n_parts, nlags, _ptr(edges_t),
+                                          _ptr(sums[0]), _ptr(sums[1]), _ptr(count), _stream()), "cmx_variogram_bins")
+        if dist is not None:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
         sums_h = sums.cpu().numpy()
         count_h = count.cpu().numpy()
     good = count_h > 0

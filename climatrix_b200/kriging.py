@@ -118,6 +118,9 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
     dtype : "float64" | "float32"      (new) dtype the result is stored in (values, normalisation and solves stay
                                        float64, so float32 output differs from float64 by its final rounding only)
     device : torch device              (new)
+    devices : list of devices          (new) moving window: shard the target rows over several GPUs of this process
+    group : torch.distributed group    (new) moving window, one process per GPU (torchrun): pair-range-sharded
+                                       variogram + all-reduce, row bands, NCCL all-gather; every rank returns the field
     """
 
     NAME: ClassVar[str] = "ok"
@@ -135,7 +138,7 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
                  anisotropy_scaling: float | None = None, coordinates_type: str | None = None,
                  variogram_model: str | None = None, pseudo_inv: bool = False, *,
                  n_closest_points: int | None = None, k: int | None = None, dtype="float64", device=None,
-                 return_variance: bool = False):
+                 devices=None, group=None, return_variance: bool = False):
         super().__init__(dataset, target_domain)
         extra = extra_dimensions(dataset.domain)
         if extra:
@@ -167,6 +170,10 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
         if self.dtype not in ("float64", "float32"):
             raise TypeError("dtype must be float64 or float32")
         self.device = device
+        self.devices = list(devices) if devices else None
+        self.group = group
+        if self.devices and group is not None:
+            raise ValueError("give either devices= (one process) or group= (one process per GPU), not both")
         # pykrige's execute() also returns the kriging variance, which climatrix drops (kriging.py:236); with
         # return_variance=True the moving-window paths keep it in ``self.variance_`` (target shape, data units^2)
         self.return_variance = bool(return_variance)
@@ -181,7 +188,7 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
 
         from . import kernels
 
-        dev = kernels._require_cuda(self.device)
+        dev = kernels._require_cuda(self.devices[0] if self.devices else self.device)
         src, tgt = self.dataset.domain, self.target_domain
         if self.backend is None:  # kriging.py:193-204
             self.backend = (
@@ -225,7 +232,8 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
             xs = torch.as_tensor(x_adj).to(dev)
             ys = torch.as_tensor(y_adj).to(dev)
             zs = torch.as_tensor(np.ascontiguousarray(z, dtype=np.float64)).to(dev)
-            lags, semivariance, _ = kernels.empirical_variogram(xs, ys, zs, self.nlags, geographic=geographic)
+            lags, semivariance, _ = kernels.empirical_variogram(xs, ys, zs, self.nlags, geographic=geographic,
+                                                                group=self.group)
             params = fit_variogram(lags, semivariance, self.variogram_model)
             self.lags, self.semivariance, self.variogram_model_parameters = lags, semivariance, params
 
@@ -271,21 +279,30 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
                 else:
                     tx, _ = _anisotropy(xpts, np.full_like(xpts, yc), xc, yc, scaling)
                     _, ty = _anisotropy(np.full_like(ypts, xc), ypts, xc, yc, scaling)
-                res = kernels.ok_moving_window(
-                    xs, ys, zs, tx, ty, not sparse_target, k=self.n_closest_points,
-                    variogram_model=self.variogram_model, params=params, exact_values=True,
-                    out_scale=float(v_std), out_shift=float(v_mean), dtype=tdtype,
-                    return_sigmasq=self.return_variance,
-                )
-                out, nsing = res[0], res[-1]
-                sig = res[1] if self.return_variance else None
-                n_sing = int(nsing.item())
+                mw = dict(k=self.n_closest_points, variogram_model=self.variogram_model, params=params,
+                          out_scale=float(v_std), out_shift=float(v_mean), dtype=tdtype,
+                          return_sigmasq=self.return_variance)
+                if self.devices and len(self.devices) > 1:
+                    from .sharding import ok_on_devices
+
+                    values, sig, n_sing = ok_on_devices(x_adj, y_adj, z, tx, ty, not sparse_target, devices=self.devices, **mw)
+                elif self.group is not None:
+                    from .sharding import distributed_ok
+
+                    out, sig, n_sing = distributed_ok(xs, ys, zs, torch.as_tensor(tx).to(dev), torch.as_tensor(ty).to(dev),
+                                                      not sparse_target, group=self.group, **mw)
+                    values = out.cpu().numpy()
+                else:
+                    res = kernels.ok_moving_window(xs, ys, zs, tx, ty, not sparse_target, exact_values=True, **mw)
+                    out, nsing = res[0], res[-1]
+                    sig = res[1] if self.return_variance else None
+                    n_sing = int(nsing.item())
+                    values = out.cpu().numpy()
                 if n_sing:
                     # pykrige raises LinAlgError from scipy.linalg.solve on a singular window
                     raise np.linalg.LinAlgError(
                         f"{n_sing} kriging windows are singular (duplicate sample coordinates among the neighbours)"
                     )
-                values = out.cpu().numpy()
             else:
                 sig = None
                 values = self._global(torch, dev, xs, ys, zs, xpts, ypts, sparse_target, xc, yc, scaling, params,
@@ -293,7 +310,8 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
             if self.return_variance and sig is not None:
                 # sigma^2 comes out in standardised units (values were z-scored): back to data units^2
                 shape = (ypts.size, xpts.size) if not sparse_target else (xpts.size,)
-                self.variance_ = (sig.double().cpu().numpy() * float(v_std) ** 2).reshape(shape)
+                sig_h = sig if isinstance(sig, np.ndarray) else sig.double().cpu().numpy()
+                self.variance_ = (np.asarray(sig_h, dtype=np.float64) * float(v_std) ** 2).reshape(shape)
 
         log.debug("Reconstruction completed.")
         values = np.asarray(values, dtype=np.float64 if self.dtype == "float64" else np.float32)

@@ -5,12 +5,15 @@ contiguous latitude-row bands of the dense target grid (or index ranges of a
 sparse target), SURVEY.md section 8e.  The only exchange step is the gather of
 the output slabs.
 
-* ``idw_on_devices``   -- host arrays in, host array out; used by the
+* ``idw_on_devices`` / ``ok_on_devices`` -- host arrays in, host array out; used by the
   reconstructor classes.  ``devices=[...]`` runs the bands concurrently on
-  several GPUs of this process.
+  several GPUs of this process: the samples cross PCIe once (to the first device) and reach the
+  others over NVLink peer copies, every band is launched asynchronously and its result streams
+  into its columns of one page-locked host array.
 * ``distributed_idw`` / ``distributed_ok`` -- one process per GPU under
   ``torchrun``: every rank computes its band with the CUDA kernels and the slabs
-  are all-gathered over NCCL (NVLink/NVSwitch).  The band computation is
+  are all-gathered over NCCL (NVLink/NVSwitch) or, for IDW batches, stored by the weighting kernel
+  itself into the ranks' symmetric-memory buffers.  The band computation is
   injectable so that the partition/gather logic is testable on CPU with gloo.
 """
 
@@ -20,7 +23,8 @@ from typing import Callable
 
 import numpy as np
 
-__all__ = ["row_shards", "idw_on_devices", "distributed_idw", "distributed_bands", "assemble_bands"]
+__all__ = ["row_shards", "idw_on_devices", "ok_on_devices", "distributed_idw", "distributed_ok", "distributed_bands",
+           "assemble_bands", "release_host_memory"]
 
 
 def row_shards(n_rows: int, parts: int) -> list[tuple[int, int]]:
@@ -60,22 +64,97 @@ def idw_on_devices(s_lat, s_lon, values, t_lat, t_lon, grid: bool, *, k: int, po
                 return _to_host(out), _to_host(dist), _to_host(idx)
             return _to_host(res)
 
-    # several GPUs driven from this process: launch every band, then collect
+    # several GPUs driven from this process: every band is launched before any result is awaited
     devs = [kernels._require_cuda(d) for d in devices]
-    n_rows = len(t_lat)
+    if return_neighbours:
+        raise ValueError("return_neighbours is not available with several devices")
+    if not isinstance(values, torch.Tensor):
+        values = torch.as_tensor(np.ascontiguousarray(values))
+    n = len(s_lat)
+    vals, n_batch, layout_code = kernels._values_layout(values, n, layout)
+    lay = None if n_batch == 1 and vals.dim() == 1 else ("sample_major" if layout_code == 1 else "batch_major")
+
+    def band(dev, rep, r0, r1):
+        s_lat_d, s_lon_d, vals_d, t_lat_d, t_lon_d = rep
+        targets = kernels.Targets(t_lat_d[r0:r1].contiguous(), t_lon_d if grid else t_lon_d[r0:r1].contiguous(), grid)
+        return kernels.idw(s_lat_d, s_lon_d, vals_d, targets, k=k, power=power, k_min=k_min, dtype=dtype, layout=lay)
+
+    host_inputs = [np.ascontiguousarray(s_lat, dtype=np.float64), np.ascontiguousarray(s_lon, dtype=np.float64), vals.to(dtype),
+                   np.ascontiguousarray(t_lat, dtype=np.float64), np.ascontiguousarray(t_lon, dtype=np.float64)]
+    n_cols = len(t_lon) if grid else 1
+    out = _bands_on_devices(devs, host_inputs, band, len(t_lat), n_cols, n_batch, dtype)
+    return out if vals.dim() == 2 else out.reshape(-1)
+
+
+def _bands_on_devices(devs, host_inputs, band_fn, n_rows: int, n_cols: int, n_batch: int, dtype):
+    """Row bands of one job on several GPUs of this process.
+
+    ``host_inputs``: NumPy arrays / CPU tensors every device needs (samples, values, target axes).  They are
+    uploaded ONCE, to the first device, and replicated to the others by peer copies (NVLink, asynchronous to the
+    host).  ``band_fn(device, replicas, r0, r1)`` launches the band's kernels on ``device`` and returns its
+    ``[n_batch, (r1 - r0) * n_cols]`` device tensor.  Nothing blocks until every band is in flight; each result is
+    then copied (one strided DMA per device, all concurrently) into its columns of a page-locked ``[n_batch, M]`` array.
+    """
+    import torch
+
+    from . import _lib
+
+    lib = _lib.load()
+    primary = devs[0]
+    with torch.cuda.device(primary):
+        first = [torch.as_tensor(a).to(primary, non_blocking=True) for a in host_inputs]
     bands = row_shards(n_rows, len(devs))
-    pending = []
+    m_total = n_rows * n_cols
+    esize = 8 if dtype == torch.float64 else 4
+    try:
+        host = torch.empty((n_batch, m_total), dtype=dtype, pin_memory=True)
+    except RuntimeError:
+        host = torch.empty((n_batch, m_total), dtype=dtype)
+    keep = []
     for dev, (r0, r1) in zip(devs, bands):
         if r1 == r0:
             continue
         with torch.cuda.device(dev):
-            lat_band = t_lat[r0:r1]
-            lon_band = t_lon if grid else t_lon[r0:r1]
-            targets = kernels.Targets.make(lat_band, lon_band, grid, dev)
-            out = kernels.idw(s_lat, s_lon, values, targets, k=k, power=power, k_min=k_min, dtype=dtype, layout=layout)
-            pending.append(out)
-    parts = [_to_host(o) for o in pending]
-    return np.concatenate(parts, axis=-1)
+            rep = first if dev == primary else [t.to(dev, non_blocking=True) for t in first]
+            res = band_fn(dev, rep, r0, r1).reshape(n_batch, -1)
+            m_band = (r1 - r0) * n_cols
+            stream = torch.cuda.current_stream(dev)
+            _lib.check(lib.cmx_copy_rows_to_host(host.data_ptr() + r0 * n_cols * esize, m_total * esize, res.data_ptr(),
+                                                 m_band * esize, m_band * esize, n_batch, stream.cuda_stream),
+                       "cmx_copy_rows_to_host")
+            keep.append((rep, res, stream))
+    for _, _, stream in keep:
+        stream.synchronize()
+    return host.numpy()
+
+
+def ok_on_devices(x_s, y_s, z, t_x, t_y, grid: bool, *, k: int, variogram_model: str, params, out_scale: float,
+                  out_shift: float, dtype, devices, return_sigmasq: bool = False, search=None):
+    """Moving-window kriging (kriging frame, host arrays in / out) with the target rows sharded over several GPUs
+    of this process.  Returns ``(field [M], sigmasq [M] | None, n_singular)``."""
+    import torch
+
+    from . import kernels
+
+    devs = [kernels._require_cuda(d) for d in devices]
+    n_rows = len(t_y) if grid else len(t_x)
+    n_cols = len(t_x) if grid else 1
+    counters = []
+
+    def band(dev, rep, r0, r1):
+        xs, ys, zs, tx, ty = rep
+        res = kernels.ok_moving_window(xs, ys, zs, tx if grid else tx[r0:r1].contiguous(), ty[r0:r1].contiguous(), grid,
+                                       k=k, variogram_model=variogram_model, params=params, out_scale=out_scale,
+                                       out_shift=out_shift, dtype=dtype, return_sigmasq=return_sigmasq, search=search)
+        counters.append(res[-1])
+        if return_sigmasq:  # field and variance travel together: [2, band]
+            return torch.stack((res[0], res[1]))
+        return res[0]
+
+    host_inputs = [np.ascontiguousarray(a, dtype=np.float64) for a in (x_s, y_s, z, t_x, t_y)]
+    out = _bands_on_devices(devs, host_inputs, band, n_rows, n_cols, 2 if return_sigmasq else 1, dtype)
+    n_sing = int(sum(int(c.item()) for c in counters))
+    return out[0], (out[1] if return_sigmasq else None), n_sing
 
 
 def _idw_two_bands(s_lat, s_lon, values, t_lat, t_lon, grid, *, k, power, k_min, dtype, dev, layout,
@@ -237,7 +316,7 @@ def distributed_bands(compute: Callable, n_rows: int, n_cols: int, n_batch: int,
         local = torch.empty((n_batch, 0), dtype=dtype, device=device)
     local = local.reshape(n_batch, -1)
     if gather == "none" or world == 1:
-        return local if gather == "none" else local
+        return local
     rows_max = max(b[1] - b[0] for b in bands)
     padded = torch.zeros((n_batch, rows_max * n_cols), dtype=dtype, device=device)
     padded[:, : local.shape[1]] = local
@@ -253,7 +332,9 @@ def distributed_idw(s_lat, s_lon, values, t_lat, t_lon, grid: bool, *, k: int, p
     Inputs are device tensors (or NumPy, copied once per rank).  Returns [T, M] (or [M]
     for a single slice) on this rank's device.  ``gather``: "all" (NCCL all-gather of padded slabs + re-assembly),
     "none" (keep the field sharded) or "peer" (batches on a dense grid: the weighting kernel itself stores every
-    band into all ranks' symmetric-memory buffers, no collective after it; device-resident ``values`` only).
+    band into all ranks' symmetric-memory buffers, no collective after it; host-resident values are uploaded first).
+    With "peer" the result IS this rank's cached symmetric buffer (one per shape): the next "peer" call of the same
+    shape overwrites it - ``clone()`` it to keep it.
     """
     import torch
 
@@ -286,11 +367,71 @@ def distributed_idw(s_lat, s_lon, values, t_lat, t_lon, grid: bool, *, k: int, p
             world, rank = dist.get_world_size(group), dist.get_rank(group)
             r0, r1 = row_shards(n_rows, world)[rank]
             pg = PeerGather.get(n_batch, n_rows, n_cols, dtype, dev, group)
+            if not isinstance(values, torch.Tensor) or values.device.type != "cuda":
+                # the kernel stores into peer memory: its inputs must be on the device before the barrier opens
+                values = torch.as_tensor(np.ascontiguousarray(values)).to(device=dev, dtype=dtype)
             pg.begin()
             if r1 > r0:
                 targets = kernels.Targets.make(t_lat[r0:r1], t_lon, True, dev)
                 kernels.idw(s_lat, s_lon, values, targets, k=k, power=power, k_min=k_min, dtype=dtype, layout=layout,
                             peer_out=pg.peer_out(r0))
-            return pg.finish()  # NOTE: this rank's cached symmetric buffer; clone() to keep it across calls
+            return pg.finish()
     out = distributed_bands(compute, n_rows, n_cols, n_batch, dtype=dtype, device=dev, group=group, gather=gather)
     return out[0] if single else out
+
+
+def distributed_ok(x_s, y_s, z, t_x, t_y, grid: bool, *, k: int, variogram_model: str, params, out_scale: float = 1.0,
+                   out_shift: float = 0.0, dtype=None, group=None, gather: str = "all", return_sigmasq: bool = False,
+                   compute: Callable | None = None):
+    """Moving-window ordinary kriging over all ranks of ``group`` (BASELINE config 4): samples and the fitted
+    variogram parameters replicated, target rows sharded, slabs all-gathered (8 MB at C4: NCCL).
+
+    Arguments are in the kriging frame (normalised / anisotropy-adjusted, as ``kernels.ok_moving_window`` takes
+    them); for a grid ``t_y`` are the rows.  Returns ``(field [M], sigmasq [M] | None, n_singular)`` with
+    ``n_singular`` summed over the ranks.  The variogram itself is sharded by pair range
+    (``kernels.empirical_variogram(..., group=group)``).  ``compute(r0, r1) -> (tensor [n_out, band], n_singular)``
+    replaces the CUDA band computation (CPU tests with gloo).
+    """
+    import torch
+    import torch.distributed as dist
+
+    from . import kernels
+
+    dtype = dtype or torch.float64
+    dev = kernels._require_cuda() if compute is None else torch.device("cpu")
+    n_rows = len(t_y) if grid else len(t_x)
+    n_cols = len(t_x) if grid else 1
+    n_out = 2 if return_sigmasq else 1
+    sing = []
+
+    if compute is None:
+        def compute(r0, r1):  # noqa: E306
+            res = kernels.ok_moving_window(x_s, y_s, z, t_x if grid else t_x[r0:r1], t_y[r0:r1], grid, k=k,
+                                           variogram_model=variogram_model, params=params, out_scale=out_scale,
+                                           out_shift=out_shift, dtype=dtype, return_sigmasq=return_sigmasq)
+            field = torch.stack((res[0], res[1])) if return_sigmasq else res[0].view(1, -1)
+            return field, res[-1]
+
+    def band(r0, r1):
+        if r1 == r0:
+            return None
+        field, n_sing = compute(r0, r1)
+        sing.append(n_sing)
+        return field
+
+    out = distributed_bands(band, n_rows, n_cols, n_out, dtype=dtype, device=dev, group=group, gather=gather)
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    for c in sing:
+        total += torch.as_tensor(c).to(device=dev, dtype=torch.int64).reshape(-1)[:1]
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    return out[0], (out[1] if return_sigmasq else None), int(total.item())
+
+
+def release_host_memory() -> None:
+    """Results larger than 4 MB are handed out as NumPy arrays backed by page-locked blocks of torch's caching host
+    allocator; when such an array is garbage collected its block returns to that cache and STAYS page-locked for
+    reuse.  Call this to hand the cached blocks back to the operating system."""
+    import torch
+
+    torch._C._host_emptyCache()

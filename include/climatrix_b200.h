@@ -179,16 +179,22 @@ int cmx_idw_apply_f32(const int32_t* idx, const double* dist, int64_t n_targets,
 
 /* ---- empirical variogram (pykrige core._initialize_variogram_model) ---- */
 
-/* minmax[0] = min, minmax[1] = max pair distance over all i>j pairs (device, 2 doubles). */
-int cmx_variogram_minmax(const double* x, const double* y, int64_t n, int metric,
+/*
+ * The pair set can be split over several calls / devices: the call handles share `part` of `n_parts` of the pair
+ * blocks (part = 0, n_parts = 1: everything); partial minima / maxima / sums combine by min / max / addition
+ * (one rank per GPU: an all-reduce of 2 + 3 * nlags numbers).
+ * minmax[0] = min, minmax[1] = max pair distance over this call's i>j pairs (device, 2 doubles; +inf / -inf
+ * when the share is empty).
+ */
+int cmx_variogram_minmax(const double* x, const double* y, int64_t n, int metric, int part, int n_parts,
                          double* minmax, void* stream);
 /*
  * edges[nlags+1] (device): bin n holds pairs with edges[n] <= d < edges[n+1].
  * sum_d / sum_g / count [nlags] (device) are ACCUMULATED into (zero them first);
- * g = 0.5 * (z_i - z_j)^2.
+ * g = 0.5 * (z_i - z_j)^2.  nlags <= 64 (CMX_ERR_UNSUPPORTED above; climatrix's hyper-parameter range is 4..20).
  */
-int cmx_variogram_bins(const double* x, const double* y, const double* z, int64_t n, int metric,
-                       int nlags, const double* edges,
+int cmx_variogram_bins(const double* x, const double* y, const double* z, int64_t n, int metric, int part,
+                       int n_parts, int nlags, const double* edges,
                        double* sum_d, double* sum_g, unsigned long long* count, void* stream);
 
 /* ---- ordinary kriging, moving window ---- */
@@ -296,6 +302,8 @@ int cmx_timing_read(int kind, double* total_ms, int64_t* launches);
 /* FP32 FFMA throughput of the current device, measured now (TFLOP/s, 2 flop per FMA);
  * the denominator of the K1 roofline.  Synchronous; < 0 on error. */
 double cmx_fp32_peak_tflops(void);
+/* FP64 DFMA throughput of the current device, measured now (TFLOP/s); the denominator of the K4 roofline. */
+double cmx_fp64_peak_tflops(void);
 
 #ifdef __cplusplus
 }

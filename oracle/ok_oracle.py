@@ -86,3 +86,24 @@ def ok_oracle(
     if return_model:
         return out, kriging
     return out
+
+
+def moving_window_with_parameters(x, y, z, xpoints, ypoints, style: str, *, k: int, variogram_model: str, parameters):
+    """pykrige ``execute(style, ..., backend="loop", n_closest_points=k)`` for GIVEN variogram parameters, in the
+    kriging frame (x, y already normalised; isotropic).  Skips the O(N^2) empirical variogram of the constructor -
+    which does not enter ``execute`` - so that spot checks at the BASELINE sizes (N = 50 000) stay cheap.
+    Returns ``(z, sigmasq)``."""
+    from . import pykrige_restated as pk
+
+    okr = OrdinaryKriging.__new__(OrdinaryKriging)
+    okr.X_ADJUSTED = np.asarray(x, dtype=np.float64)
+    okr.Y_ADJUSTED = np.asarray(y, dtype=np.float64)
+    okr.Z = np.asarray(z, dtype=np.float64)
+    okr.XCENTER = okr.YCENTER = 0.0
+    okr.anisotropy_scaling, okr.anisotropy_angle = 1.0, 0.0
+    okr.coordinates_type = "euclidean"
+    okr.variogram_model = variogram_model
+    okr.variogram_function = pk.VARIOGRAM_FUNCTIONS[variogram_model]
+    okr.variogram_model_parameters = np.asarray(parameters, dtype=np.float64)
+    okr.exact_values, okr.pseudo_inv, okr.pseudo_inv_type = True, False, "pinv"
+    return okr.execute(style, xpoints, ypoints, backend="loop", n_closest_points=k)

@@ -22,8 +22,8 @@ import torch  # noqa: E402
 from climatrix_b200 import _lib  # noqa: E402
 from climatrix_b200 import kernels as K  # noqa: E402
 from helpers import rel_err, synthetic_field  # noqa: E402
-from oracle import pykrige_restated as pk  # noqa: E402
-from oracle.idw_oracle import dense_points, idw_oracle, idw_oracle_batched, knn_ckdtree, sparse_points  # noqa: E402
+from oracle.idw_oracle import dense_points, idw_oracle, idw_oracle_batched, sparse_points  # noqa: E402
+from oracle.ok_oracle import moving_window_with_parameters  # noqa: E402
 
 DEV = "cuda:0"
 
@@ -134,15 +134,11 @@ def test_c4_size_k64_solve_matches_restated_pykrige_on_sampled_rows():
     out, sig, nsing = K.ok_moving_window(x, y, z, tx, ty, True, k=64, variogram_model="spherical", params=params,
                                          return_sigmasq=True)
     assert int(nsing) == 0 and out.numel() == 721 * 1440 and bool(torch.isfinite(out).all())
-    okr = pk.OrdinaryKriging.__new__(pk.OrdinaryKriging)
-    okr.__dict__.update(dict(X_ADJUSTED=x, Y_ADJUSTED=y, Z=z, XCENTER=0.0, YCENTER=0.0, anisotropy_scaling=1.0,
-                             anisotropy_angle=0.0, coordinates_type="euclidean", variogram_model="spherical",
-                             variogram_function=pk.VARIOGRAM_FUNCTIONS["spherical"], variogram_model_parameters=params,
-                             exact_values=True, pseudo_inv=False, pseudo_inv_type="pinv"))
     rows = [0, 360, 720]
     cols = np.arange(0, 1440, 5)
     gx, gy = np.meshgrid(tx[cols], ty[rows])
-    zr, sr = okr.execute("points", gx.ravel(), gy.ravel(), backend="loop", n_closest_points=64)
+    zr, sr = moving_window_with_parameters(x, y, z, gx.ravel(), gy.ravel(), "points", k=64, variogram_model="spherical",
+                                           parameters=params)
     sel = torch.as_tensor((np.asarray(rows)[:, None] * 1440 + cols[None, :]).ravel(), device=out.device)
     assert np.max(np.abs(out[sel].cpu().numpy() - zr)) <= 1e-4 * np.max(np.abs(zr))
     assert np.max(np.abs(sig[sel].cpu().numpy() - sr)) <= 1e-4 * np.max(np.abs(sr))

@@ -88,3 +88,72 @@ def test_two_rank_gather_matches_single_process(n_lat):
     for rank, same, shape in results:
         assert same, f"rank {rank} assembled a different field"
         assert shape == (3, n_lat * 9)
+
+
+def _ok_worker(rank, world, port, n_lat, q):
+    """distributed_ok on two gloo ranks: the restated pykrige stands in for K1 + K4 on each band."""
+    import warnings
+
+    from climatrix_b200.sharding import distributed_ok
+    from oracle import pykrige_restated as pk
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(11)
+        n = 200
+        x, y = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+        z = np.sin(3 * x) + 0.2 * rng.normal(size=n)
+        if n_lat > 3:  # a duplicate pair with zero nugget: singular windows are counted across ranks
+            x[1], y[1] = x[0], y[0]
+        params = [1.0, 0.5, 0.0]
+        tx, ty = np.linspace(-1, 1, 6), np.linspace(-1, 1, n_lat)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            okr = pk.OrdinaryKriging(x, y, z, variogram_model="spherical", variogram_parameters=params)
+
+        def solve(ty_band):
+            zz = np.full((len(ty_band), len(tx)), np.nan)
+            ss = np.full_like(zz, np.nan)
+            bad = 0
+            for i, yy in enumerate(ty_band):
+                for j, xx in enumerate(tx):
+                    try:
+                        with warnings.catch_warnings():
+                            warnings.simplefilter("error")
+                            a, b = okr.execute("points", [xx], [yy], backend="loop", n_closest_points=8)
+                        zz[i, j], ss[i, j] = a[0], b[0]
+                    except Exception:  # noqa: BLE001  (LinAlgError / LinAlgWarning: singular window)
+                        bad += 1
+            return zz, ss, bad
+
+        def compute(r0, r1):
+            zz, ss, bad = solve(ty[r0:r1])
+            return torch.from_numpy(np.stack((zz.ravel(), ss.ravel()))), torch.tensor([bad])
+
+        field, sig, n_sing = distributed_ok(x, y, z, tx, ty, True, k=8, variogram_model="spherical", params=params,
+                                            return_sigmasq=True, compute=compute)
+        zz, ss, bad = solve(ty)
+        same = np.array_equal(field.numpy(), zz.ravel(), equal_nan=True) and np.array_equal(sig.numpy(), ss.ravel(), equal_nan=True)
+        q.put((rank, bool(same), tuple(field.shape), n_sing == bad))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_lat", [5, 1])
+def test_two_rank_kriging_bands_match_single_process(n_lat):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ok_worker, args=(r, 2, port, n_lat, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, same, shape, counted in results:
+        assert same, f"rank {rank} assembled a different field"
+        assert shape == (n_lat * 6,)
+        assert counted, f"rank {rank}: singular windows not summed over the ranks"
