@@ -23,7 +23,7 @@ class Options(ctypes.Structure):
     """``cmx_options`` of include/climatrix_b200.h: everything optional about a call, passed explicitly."""
 
     _fields_ = [("search", c_int), ("n_peers", c_int), ("peer_out", c_void_p * MAX_PEERS), ("m_total", c_i64),
-                ("m_offset", c_i64)]
+                ("m_offset", c_i64), ("params_on_device", c_int)]
 
 
 SEARCH_AUTO, SEARCH_BRUTE, SEARCH_BINNED = 0, 1, 2
@@ -44,10 +44,14 @@ SIGNATURES = {
     "cmx_idw_apply_f64": (c_int, [_P, _P, c_i64, c_int, _P, c_i64, c_i64, c_int, c_int, c_int, c_double, _P, _P, _OPT, _P]),
     "cmx_idw_apply_f32": (c_int, [_P, _P, c_i64, c_int, _P, c_i64, c_i64, c_int, c_int, c_int, c_double, _P, _P, _OPT, _P]),
     "cmx_variogram_minmax": (c_int, [_P, _P, c_i64, c_int, c_int, c_int, _P, _P]),
-    "cmx_variogram_bins": (c_int, [_P, _P, _P, c_i64, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
+    "cmx_variogram_workspace_bytes": (c_size_t, [c_int]),
+    "cmx_variogram_bins": (c_int, [_P, _P, _P, c_i64, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "cmx_variogram_fit_host": (c_int, [c_int, ctypes.POINTER(c_double), ctypes.POINTER(c_double), c_int, ctypes.POINTER(c_double), ctypes.POINTER(c_int)]),
+    "cmx_variogram_edges": (c_int, [_P, c_int, _P, _P]),
+    "cmx_variogram_fit": (c_int, [c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "cmx_ok_workspace_bytes": (c_size_t, [c_int, c_i64]),
-    "cmx_ok_mw_f64": (c_int, [_P, _P, _P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, c_int, c_int, ctypes.POINTER(c_double), c_int, c_double, c_double, _P, _P, _P, _P, c_size_t, _OPT, _P]),
-    "cmx_ok_mw_f32": (c_int, [_P, _P, _P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, c_int, c_int, ctypes.POINTER(c_double), c_int, c_double, c_double, _P, _P, _P, _P, c_size_t, _OPT, _P]),
+    "cmx_ok_mw_f64": (c_int, [_P, _P, _P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, c_int, c_int, _P, c_int, c_double, c_double, _P, _P, _P, _P, c_size_t, _OPT, _P]),
+    "cmx_ok_mw_f32": (c_int, [_P, _P, _P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, c_int, c_int, _P, c_int, c_double, c_double, _P, _P, _P, _P, c_size_t, _OPT, _P]),
     "cmx_timing_enable": (None, [c_int]),
     "cmx_timing_reset": (None, []),
     "cmx_timing_read": (c_int, [c_int, ctypes.POINTER(c_double), ctypes.POINTER(c_i64)]),
@@ -55,8 +59,8 @@ SIGNATURES = {
     "cmx_fp64_peak_tflops": (c_double, []),
     "cmx_knn3": (c_int, [_P, _P, _P, c_i64, _P, _P, _P, c_i64, c_int, _P, _P, _P]),
     "cmx_ok_solve_workspace_bytes": (c_size_t, [c_i64]),
-    "cmx_ok_solve_f64": (c_int, [_P, _P, _P, c_i64, _P, _P, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_double), c_int, c_double, c_double, _P, _P, _P, _P, c_size_t, _P]),
-    "cmx_ok_solve_f32": (c_int, [_P, _P, _P, c_i64, _P, _P, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_double), c_int, c_double, c_double, _P, _P, _P, _P, c_size_t, _P]),
+    "cmx_ok_solve_f64": (c_int, [_P, _P, _P, c_i64, _P, _P, c_i64, c_int, c_int, c_int, _P, c_int, c_double, c_double, _P, _P, _P, _P, c_size_t, _OPT, _P]),
+    "cmx_ok_solve_f32": (c_int, [_P, _P, _P, c_i64, _P, _P, c_i64, c_int, c_int, c_int, _P, c_int, c_double, c_double, _P, _P, _P, _P, c_size_t, _OPT, _P]),
     "cmx_knn_plan": (c_int, [c_i64, c_i64, c_i64, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "cmx_copy_rows_to_host": (c_int, [_P, c_size_t, _P, c_size_t, c_size_t, c_size_t, _P]),
     "cmx_launch_count": (c_i64, []),

@@ -12,10 +12,13 @@ thread_local char g_cuda_err[256] = "";
 
 void note_launch() { ++g_launches; }
 
-int read_options(const cmx_options* opt, int* search, PeerOut* peers) {
+int read_options(const cmx_options* opt, int* search, PeerOut* peers, int* params_on_device) {
     if (search) *search = CMX_SEARCH_AUTO;
     if (peers) peers->n = 0;
+    if (params_on_device) *params_on_device = 0;
     if (!opt) return CMX_OK;
+    if (opt->params_on_device && !params_on_device) return CMX_ERR_UNSUPPORTED;
+    if (params_on_device) *params_on_device = opt->params_on_device != 0;
     if (opt->search != CMX_SEARCH_AUTO && opt->search != CMX_SEARCH_BRUTE && opt->search != CMX_SEARCH_BINNED)
         return CMX_ERR_BAD_ARG;
     if (search) *search = opt->search;

@@ -24,7 +24,7 @@ struct PeerOut {
     long long m_total, m_off;
 };
 // validated copy of the caller's options (NULL -> defaults); returns CMX_OK or CMX_ERR_BAD_ARG
-int read_options(const cmx_options* opt, int* search, PeerOut* peers);
+int read_options(const cmx_options* opt, int* search, PeerOut* peers, int* params_on_device = nullptr);
 int cuda_fail(cudaError_t e);       // records text, returns CMX_ERR_CUDA
 int check_launch();                 // cudaGetLastError() -> CMX_OK / CMX_ERR_CUDA
 int sm_count();                     // SMs of the current device (cached)

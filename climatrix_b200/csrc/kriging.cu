@@ -37,6 +37,7 @@ struct OkArgs {
     int k;
     int model;
     double p0, p1, p2;
+    const double* params_dev;  // non-null: the three parameters live in device memory (written by the fit kernel)
     int exact_values;
     int metric;  // CMX_METRIC_EUCLIDEAN: d2 = squared Euclidean; GEOGRAPHIC: d2 = squared chord, s_x = lon, s_y = lat (degrees)
     double out_scale, out_shift;
@@ -48,6 +49,18 @@ struct OkArgs {
     const int* list_count;
 };
 
+// the variogram parameters: kernel arguments, or three doubles in device memory
+__device__ __forceinline__ void load_params(const OkArgs& a, double& p0, double& p1, double& p2) {
+    if (a.params_dev) {
+        p0 = a.params_dev[0];
+        p1 = a.params_dev[1];
+        p2 = a.params_dev[2];
+    } else {
+        p0 = a.p0;
+        p1 = a.p1;
+        p2 = a.p2;
+    }
+}
 __device__ __forceinline__ long long window_count(const OkArgs& a) { return a.list ? (long long)*a.list_count : a.M; }
 __device__ __forceinline__ long long window_target(const OkArgs& a, long long w) { return a.list ? (long long)a.list[w] : w; }
 __device__ __forceinline__ void store_window(const OkArgs& a, long long m, double res, double var) {
@@ -100,6 +113,8 @@ __global__ void __launch_bounds__(256) ok_solve_kernel(const OkArgs a, int warps
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     // per warp: matrix (k+2) columns x LD rows, then neighbour coordinates, then pivot rows
+    double P0, P1, P2;
+    load_params(a, P0, P1, P2);
     const size_t per_warp = (size_t)(k + 2) * LD * sizeof(double) + 2 * LD * sizeof(double) + LD * sizeof(int);
     unsigned char* base = smem_raw + (size_t)warp * per_warp;
     double* mat = reinterpret_cast<double*>(base);
@@ -129,7 +144,7 @@ __global__ void __launch_bounds__(256) ok_solve_kernel(const OkArgs a, int warps
                 my[e] = a.s_y[id];
                 mz[e] = a.z[id];
                 const double bd = window_distance(a.metric, a.d2[m * k + r]);
-                double b = -gamma_of(a.model, a.p0, a.p1, a.p2, bd);
+                double b = -gamma_of(a.model, P0, P1, P2, bd);
                 if (a.exact_values && fabs(bd) <= OK_EPS) b = 0.0;
                 borig[e] = b;
                 cx[r] = mx[e];
@@ -147,7 +162,7 @@ __global__ void __launch_bounds__(256) ok_solve_kernel(const OkArgs a, int warps
                 const int r = e * 32 + lane;
                 if (r < k) {
                     const double d = sample_distance(a.metric, mx[e], my[e], xj, yj);
-                    mat[(size_t)j * LD + r] = (r == j) ? 0.0 : -gamma_of(a.model, a.p0, a.p1, a.p2, d);
+                    mat[(size_t)j * LD + r] = (r == j) ? 0.0 : -gamma_of(a.model, P0, P1, P2, d);
                 }
             }
         }
@@ -274,6 +289,8 @@ __global__ void __launch_bounds__(512) ok_solve_team_kernel(const OkArgs a, int 
     const int warp = threadIdx.x >> 5;
     const int team = warp / W, wsub = warp % W;
     const int r = wsub * 32 + lane;  // my row (and my column in the final extraction)
+    double P0, P1, P2;
+    load_params(a, P0, P1, P2);
     const size_t per_team = (size_t)(k + 2) * LD * sizeof(double) + 2 * LD * sizeof(double) + LD * sizeof(int) +
                             2 * W * 16 + 4 * W * sizeof(double);
     unsigned char* base = smem_raw + (size_t)team * per_team;
@@ -303,7 +320,7 @@ __global__ void __launch_bounds__(512) ok_solve_team_kernel(const OkArgs a, int 
             my = a.s_y[id];
             mz = a.z[id];
             const double bd = window_distance(a.metric, a.d2[m * k + r]);
-            double b = -gamma_of(a.model, a.p0, a.p1, a.p2, bd);
+            double b = -gamma_of(a.model, P0, P1, P2, bd);
             if (a.exact_values && fabs(bd) <= OK_EPS) b = 0.0;
             borig = b;
             cx[r] = mx;
@@ -315,7 +332,7 @@ __global__ void __launch_bounds__(512) ok_solve_team_kernel(const OkArgs a, int 
         if (r < k) {
             for (int j = 0; j < k; ++j) {
                 const double d = sample_distance(a.metric, mx, my, cx[j], cy[j]);
-                mat[(size_t)j * LD + r] = (r == j) ? 0.0 : -gamma_of(a.model, a.p0, a.p1, a.p2, d);
+                mat[(size_t)j * LD + r] = (r == j) ? 0.0 : -gamma_of(a.model, P0, P1, P2, d);
             }
         }
         bool done = false, singular = false;
@@ -625,7 +642,9 @@ __global__ void __launch_bounds__(TEAMS * ((KC + 31) / 32) * 32, KC > 32 ? 3 : 4
         else
             __syncwarp();
     };
-    const VarioConst vc = vario_const(A.model, A.p0, A.p1, A.p2);
+    double P0, P1, P2;
+    load_params(A, P0, P1, P2);
+    const VarioConst vc = vario_const(A.model, P0, P1, P2);
 
     const long long total_teams = (long long)gridDim.x * TEAMS;
     const long long n_windows = window_count(A);
@@ -819,9 +838,9 @@ inline size_t chol_scratch_bytes(long long M) { return ((size_t)(M > 0 ? M : 0) 
 
 // K4 on an existing neighbour table.  scratch (chol_scratch_bytes(M), may be null): hand-over list of the Cholesky path.
 int solve_table(const double* s_x, const double* s_y, const double* z, long long n, const int* idx, const double* d2,
-                long long M, int metric, int k, int model, const double* params, int exact_values, double out_scale,
-                double out_shift, void* out, void* sigmasq, int out_is_f32, int32_t* n_singular, void* scratch,
-                size_t scratch_bytes, cudaStream_t stream) {
+                long long M, int metric, int k, int model, const double* params, int params_on_device, int exact_values,
+                double out_scale, double out_shift, void* out, void* sigmasq, int out_is_f32, int32_t* n_singular,
+                void* scratch, size_t scratch_bytes, cudaStream_t stream) {
     if (M == 0) return CMX_OK;
     if (M > 0x7fffffffLL) return CMX_ERR_TOO_MANY;
     OkArgs a;
@@ -835,9 +854,10 @@ int solve_table(const double* s_x, const double* s_y, const double* z, long long
     a.n = n;
     a.k = k;
     a.model = model;
-    a.p0 = params[0];
-    a.p1 = params[1];
-    a.p2 = params[2];
+    a.params_dev = params_on_device ? params : nullptr;
+    a.p0 = params_on_device ? 0.0 : params[0];
+    a.p1 = params_on_device ? 0.0 : params[1];
+    a.p2 = params_on_device ? 0.0 : params[2];
     a.exact_values = exact_values;
     a.metric = metric;
     a.out_scale = out_scale;
@@ -877,13 +897,16 @@ int solve_table(const double* s_x, const double* s_y, const double* z, long long
 int solve_entry(const double* s_x, const double* s_y, const double* z, int64_t n, const int32_t* idx, const double* d2,
                 int64_t M, int metric, int k, int model, const double* params, int exact_values, double out_scale,
                 double out_shift, void* out, void* sigmasq, int out_is_f32, int32_t* n_singular, void* ws,
-                size_t ws_bytes, void* stream) {
+                size_t ws_bytes, const cmx_options* options, void* stream) {
+    int params_on_device = 0;
+    const int orc = read_options(options, nullptr, nullptr, &params_on_device);
+    if (orc != CMX_OK) return orc;
     if (!s_x || !s_y || !z || !idx || !d2 || !params || !out || n < 1 || M < 0 || k < 1) return CMX_ERR_BAD_ARG;
     if (k > CMX_MAX_K) return CMX_ERR_K_TOO_LARGE;
     if (model < CMX_VARIOGRAM_LINEAR || model > CMX_VARIOGRAM_EXPONENTIAL) return CMX_ERR_UNSUPPORTED;
     if (metric != CMX_METRIC_EUCLIDEAN && metric != CMX_METRIC_GEOGRAPHIC) return CMX_ERR_UNSUPPORTED;
-    return solve_table(s_x, s_y, z, n, idx, d2, M, metric, k, model, params, exact_values, out_scale, out_shift, out,
-                       sigmasq, out_is_f32, n_singular, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+    return solve_table(s_x, s_y, z, n, idx, d2, M, metric, k, model, params, params_on_device, exact_values, out_scale,
+                       out_shift, out, sigmasq, out_is_f32, n_singular, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int ok_entry(const double* s_x, const double* s_y, const double* z, int64_t n, const double* t_x, int64_t n_x,
@@ -891,8 +914,8 @@ int ok_entry(const double* s_x, const double* s_y, const double* z, int64_t n, c
              int exact_values, double out_scale, double out_shift, void* out, void* sigmasq, int out_is_f32,
              int32_t* n_singular, void* workspace, size_t workspace_bytes, const cmx_options* options, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    int search = CMX_SEARCH_AUTO;
-    const int orc = read_options(options, &search, nullptr);
+    int search = CMX_SEARCH_AUTO, params_on_device = 0;
+    const int orc = read_options(options, &search, nullptr, &params_on_device);
     if (orc != CMX_OK) return orc;
     if (!s_x || !s_y || !z || !t_x || !t_y || !params || !out) return CMX_ERR_BAD_ARG;
     if (model < CMX_VARIOGRAM_LINEAR || model > CMX_VARIOGRAM_EXPONENTIAL) return CMX_ERR_UNSUPPORTED;
@@ -931,8 +954,9 @@ int ok_entry(const double* s_x, const double* s_y, const double* z, int64_t n, c
     if (rc != CMX_OK) return rc;
     if (M == 0) return CMX_OK;
 
-    return solve_table(s_x, s_y, z, n, idx_tab, d2_tab, M, CMX_METRIC_EUCLIDEAN, k, model, params, exact_values,
-                       out_scale, out_shift, out, sigmasq, out_is_f32, n_singular, list_scratch, list_bytes, stream);
+    return solve_table(s_x, s_y, z, n, idx_tab, d2_tab, M, CMX_METRIC_EUCLIDEAN, k, model, params, params_on_device,
+                       exact_values, out_scale, out_shift, out, sigmasq, out_is_f32, n_singular, list_scratch, list_bytes,
+                       stream);
 }
 
 }  // namespace
@@ -965,16 +989,16 @@ int cmx_ok_mw_f32(const double* s_x, const double* s_y, const double* z, int64_t
 int cmx_ok_solve_f64(const double* s_x, const double* s_y, const double* z, int64_t n, const int32_t* idx,
                      const double* d2, int64_t M, int metric, int k, int model, const double params[3],
                      int exact_values, double out_scale, double out_shift, double* out, double* sigmasq,
-                     int32_t* n_singular, void* ws, size_t ws_bytes, void* stream) {
+                     int32_t* n_singular, void* ws, size_t ws_bytes, const cmx_options* options, void* stream) {
     return cmx::solve_entry(s_x, s_y, z, n, idx, d2, M, metric, k, model, params, exact_values, out_scale, out_shift,
-                            out, sigmasq, 0, n_singular, ws, ws_bytes, stream);
+                            out, sigmasq, 0, n_singular, ws, ws_bytes, options, stream);
 }
 int cmx_ok_solve_f32(const double* s_x, const double* s_y, const double* z, int64_t n, const int32_t* idx,
                      const double* d2, int64_t M, int metric, int k, int model, const double params[3],
                      int exact_values, double out_scale, double out_shift, float* out, float* sigmasq,
-                     int32_t* n_singular, void* ws, size_t ws_bytes, void* stream) {
+                     int32_t* n_singular, void* ws, size_t ws_bytes, const cmx_options* options, void* stream) {
     return cmx::solve_entry(s_x, s_y, z, n, idx, d2, M, metric, k, model, params, exact_values, out_scale, out_shift,
-                            out, sigmasq, 1, n_singular, ws, ws_bytes, stream);
+                            out, sigmasq, 1, n_singular, ws, ws_bytes, options, stream);
 }
 
 }  // extern "C"

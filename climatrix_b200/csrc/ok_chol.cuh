@@ -170,7 +170,9 @@ ok_chol_kernel(const OkArgs A, int* __restrict__ fail_list, int* __restrict__ fa
     double* tri = ext + 3 * KC;                             // [TRI]         gamma(i, m), m < i, at i (i - 1) / 2 + m
     const int k = A.k;
     const int k4 = (k + 3) & ~3;
-    const VarioConst vc = vario_const(A.model, A.p0, A.p1, A.p2);
+    double P0, P1, P2;
+    load_params(A, P0, P1, P2);
+    const VarioConst vc = vario_const(A.model, P0, P1, P2);
 
     // the trip count is the same for every warp of the CTA (phase barriers inside): a warp beyond the last window
     // recomputes window M - 1 and stores nothing

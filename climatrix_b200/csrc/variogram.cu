@@ -14,6 +14,7 @@
 // memory.  Per-thread bin accumulators live in (L1-resident) local memory, are
 // reduced over the block in shared memory and leave the CTA as one atomic per bin.
 #include "common.cuh"
+#include "variogram_fit.cuh"
 
 namespace cmx {
 namespace {
@@ -103,18 +104,15 @@ __global__ void __launch_bounds__(VT) variogram_bins_kernel(const double* __rest
                                                             const double* __restrict__ z, long long n,
                                                             long long n_blocks, long long part, long long n_parts,
                                                             int nlags, const double* __restrict__ edges, double* sum_d,
-                                                            double* sum_g, unsigned long long* count) {
+                                                            double* sum_g, unsigned long long* count,
+                                                            double* __restrict__ part_d, double* __restrict__ part_g,
+                                                            unsigned long long* __restrict__ part_c) {
     __shared__ double sx[VT], sy[VT], sz[VT];
     __shared__ double s_edges[MAX_LAGS + 1];
-    __shared__ double s_sd[MAX_LAGS], s_sg[MAX_LAGS];
-    __shared__ unsigned long long s_cnt[MAX_LAGS];
+    __shared__ double s_wd[VT / 32][MAX_LAGS], s_wg[VT / 32][MAX_LAGS];
+    __shared__ unsigned s_wc[VT / 32][MAX_LAGS];
     const int tid = threadIdx.x;
     if (tid <= nlags) s_edges[tid] = edges[tid];
-    if (tid < nlags) {
-        s_sd[tid] = 0.0;
-        s_sg[tid] = 0.0;
-        s_cnt[tid] = 0ull;
-    }
     double acc_d[MAX_LAGS], acc_g[MAX_LAGS];
     unsigned acc_c[MAX_LAGS];
     for (int b = 0; b < nlags; ++b) {
@@ -160,24 +158,95 @@ __global__ void __launch_bounds__(VT) variogram_bins_kernel(const double* __rest
             // (32-bit per-thread counters: a thread sees at most n_blocks / gridDim.x * 256 < 2^32 pairs for n < 2^31)
         }
     }
-    // block reduction per bin, then one atomic per bin and CTA
+    // Deterministic reduction: lanes by shuffles, the warps of the CTA in warp order, the CTAs (whose share of the pair
+    // blocks is fixed by the launch geometry) in CTA order by variogram_reduce_kernel - no floating-point atomics, so
+    // the sums, the fitted parameters and the kriged field are reproducible from run to run.  Without scratch
+    // (part_d == nullptr) the CTA results are accumulated with atomics as before.
     for (int b = 0; b < nlags; ++b) {
         const double d = warp_sum(acc_d[b]);
         const double g = warp_sum(acc_g[b]);
         unsigned c = acc_c[b];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
-        if ((tid & 31) == 0 && c) {
-            atomicAdd(&s_sd[b], d);
-            atomicAdd(&s_sg[b], g);
-            atomicAdd(&s_cnt[b], (unsigned long long)c);
+        if ((tid & 31) == 0) {
+            s_wd[tid >> 5][b] = d;
+            s_wg[tid >> 5][b] = g;
+            s_wc[tid >> 5][b] = c;
         }
     }
     __syncthreads();
-    if (tid < nlags && s_cnt[tid]) {
-        atomicAdd(&sum_d[tid], s_sd[tid]);
-        atomicAdd(&sum_g[tid], s_sg[tid]);
-        atomicAdd(&count[tid], s_cnt[tid]);
+    if (tid < nlags) {
+        double d = 0.0, g = 0.0;
+        unsigned long long c = 0ull;
+        for (int w = 0; w < VT / 32; ++w) {
+            d += s_wd[w][tid];
+            g += s_wg[w][tid];
+            c += s_wc[w][tid];
+        }
+        if (part_d) {
+            part_d[(size_t)blockIdx.x * nlags + tid] = d;
+            part_g[(size_t)blockIdx.x * nlags + tid] = g;
+            part_c[(size_t)blockIdx.x * nlags + tid] = c;
+        } else if (c) {
+            atomicAdd(&sum_d[tid], d);
+            atomicAdd(&sum_g[tid], g);
+            atomicAdd(&count[tid], c);
+        }
+    }
+}
+
+// sums the per-CTA partial results in CTA order and ADDS them to the outputs (one thread per bin)
+__global__ void variogram_reduce_kernel(const double* __restrict__ part_d, const double* __restrict__ part_g,
+                                        const unsigned long long* __restrict__ part_c, int n_ctas, int nlags, double* sum_d,
+                                        double* sum_g, unsigned long long* count) {
+    const int b = threadIdx.x;
+    if (b >= nlags) return;
+    double d = 0.0, g = 0.0;
+    unsigned long long c = 0ull;
+    for (int i = 0; i < n_ctas; ++i) {
+        d += part_d[(size_t)i * nlags + b];
+        g += part_g[(size_t)i * nlags + b];
+        c += part_c[(size_t)i * nlags + b];
+    }
+    sum_d[b] += d;
+    sum_g[b] += g;
+    count[b] += c;
+}
+
+// bin edges exactly as pykrige builds them: dmin + i * dd for i < nlags, last edge dmax + 0.001
+__global__ void variogram_edges_kernel(const double* __restrict__ minmax, int nlags, double* __restrict__ edges) {
+    const int i = threadIdx.x;
+    const double dmin = minmax[0], dmax = minmax[1];
+    const double dd = __ddiv_rn(__dsub_rn(dmax, dmin), (double)nlags);
+    if (i < nlags) edges[i] = __dadd_rn(dmin, __dmul_rn((double)i, dd));
+    if (i == nlags) edges[i] = __dadd_rn(dmax, 0.001);
+}
+
+// lags / semivariances of the non-empty bins, then the TRF fit - one thread (the problem has <= 64 residuals and
+// 2-3 parameters; the iteration is a serial chain of dependent double-precision operations)
+__global__ void variogram_fit_kernel(int model, int nlags, const double* __restrict__ sum_d, const double* __restrict__ sum_g,
+                                     const unsigned long long* __restrict__ count, double* __restrict__ params,
+                                     double* __restrict__ lags_out, double* __restrict__ sv_out, int* __restrict__ info) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double lags[vfit::MAXM], sv[vfit::MAXM];
+    int m = 0;
+    for (int b = 0; b < nlags; ++b) {
+        if (count[b] > 0ull) {
+            lags[m] = sum_d[b] / (double)count[b];
+            sv[m] = sum_g[b] / (double)count[b];
+            ++m;
+        }
+    }
+    int nfev = 0;
+    const int status = m > 0 ? vfit::variogram_fit_trf(model, m, lags, sv, params, &nfev) : -1;
+    for (int b = 0; b < nlags; ++b) {
+        if (lags_out) lags_out[b] = b < m ? lags[b] : 0.0;
+        if (sv_out) sv_out[b] = b < m ? sv[b] : 0.0;
+    }
+    if (info) {
+        info[0] = status;
+        info[1] = m;
+        info[2] = nfev;
     }
 }
 
@@ -185,6 +254,35 @@ __global__ void __launch_bounds__(VT) variogram_bins_kernel(const double* __rest
 }  // namespace cmx
 
 extern "C" {
+
+int cmx_variogram_fit_host(int model, const double* lags, const double* semivariance, int n, double params_out[3],
+                           int* nfev_out) {
+    if (!lags || !semivariance || !params_out || n < 1 || n > cmx::vfit::MAXM) return CMX_ERR_BAD_ARG;
+    if (model < CMX_VARIOGRAM_LINEAR || model > CMX_VARIOGRAM_EXPONENTIAL) return CMX_ERR_UNSUPPORTED;
+    const int status = cmx::vfit::variogram_fit_trf(model, n, lags, semivariance, params_out, nfev_out);
+    return status < 0 ? CMX_ERR_BAD_ARG : status;
+}
+
+int cmx_variogram_edges(const double* minmax, int nlags, double* edges, void* stream_) {
+    using namespace cmx;
+    if (!minmax || !edges || nlags < 1) return CMX_ERR_BAD_ARG;
+    if (nlags > MAX_LAGS) return CMX_ERR_UNSUPPORTED;
+    variogram_edges_kernel<<<1, MAX_LAGS + 1, 0, static_cast<cudaStream_t>(stream_)>>>(minmax, nlags, edges);
+    note_launch();
+    return check_launch();
+}
+
+int cmx_variogram_fit(int model, int nlags, const double* sum_d, const double* sum_g, const unsigned long long* count,
+                      double* params_out, double* lags_out, double* semivariance_out, int32_t* info, void* stream_) {
+    using namespace cmx;
+    if (!sum_d || !sum_g || !count || !params_out || nlags < 1) return CMX_ERR_BAD_ARG;
+    if (nlags > MAX_LAGS) return CMX_ERR_UNSUPPORTED;
+    if (model < CMX_VARIOGRAM_LINEAR || model > CMX_VARIOGRAM_EXPONENTIAL) return CMX_ERR_UNSUPPORTED;
+    variogram_fit_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream_)>>>(model, nlags, sum_d, sum_g, count, params_out,
+                                                                           lags_out, semivariance_out, info);
+    note_launch();
+    return check_launch();
+}
 
 int cmx_variogram_minmax(const double* x, const double* y, int64_t n, int metric, int part, int n_parts,
                          double* minmax, void* stream_) {
@@ -206,9 +304,14 @@ int cmx_variogram_minmax(const double* x, const double* y, int64_t n, int metric
     return check_launch();
 }
 
+size_t cmx_variogram_workspace_bytes(int nlags) {
+    if (nlags < 1 || nlags > cmx::MAX_LAGS) return 0;
+    return (size_t)cmx::sm_count() * 8 * nlags * (2 * sizeof(double) + sizeof(unsigned long long)) + 256;
+}
+
 int cmx_variogram_bins(const double* x, const double* y, const double* z, int64_t n, int metric, int part,
                        int n_parts, int nlags, const double* edges, double* sum_d, double* sum_g,
-                       unsigned long long* count, void* stream_) {
+                       unsigned long long* count, void* workspace, size_t workspace_bytes, void* stream_) {
     using namespace cmx;
     if (!x || !y || !z || !edges || !sum_d || !sum_g || !count || n < 2 || nlags < 1) return CMX_ERR_BAD_ARG;
     if (n_parts < 1 || part < 0 || part >= n_parts) return CMX_ERR_BAD_ARG;
@@ -220,13 +323,28 @@ int cmx_variogram_bins(const double* x, const double* y, const double* z, int64_
     const long long mine = (n_blocks - part + n_parts - 1) / n_parts;
     if (mine <= 0) return CMX_OK;
     const int grid = (int)(mine < (long long)sm_count() * 8 ? mine : (long long)sm_count() * 8);
+    // scratch for the deterministic two-stage reduction: [grid][nlags] x (sum_d, sum_g, count); optional
+    double *part_d = nullptr, *part_g = nullptr;
+    unsigned long long* part_c = nullptr;
+    if (workspace) {
+        unsigned char* w = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(workspace) + 15) & ~uintptr_t(15));
+        const size_t need = (size_t)grid * nlags * (2 * sizeof(double) + sizeof(unsigned long long));
+        if (w + need > static_cast<unsigned char*>(workspace) + workspace_bytes) return CMX_ERR_WORKSPACE;
+        part_d = reinterpret_cast<double*>(w);
+        part_g = part_d + (size_t)grid * nlags;
+        part_c = reinterpret_cast<unsigned long long*>(part_g + (size_t)grid * nlags);
+    }
     if (metric == CMX_METRIC_EUCLIDEAN)
-        variogram_bins_kernel<CMX_METRIC_EUCLIDEAN>
-            <<<grid, VT, 0, stream>>>(x, y, z, n, n_blocks, part, n_parts, nlags, edges, sum_d, sum_g, count);
+        variogram_bins_kernel<CMX_METRIC_EUCLIDEAN><<<grid, VT, 0, stream>>>(x, y, z, n, n_blocks, part, n_parts, nlags, edges,
+                                                                          sum_d, sum_g, count, part_d, part_g, part_c);
     else
-        variogram_bins_kernel<CMX_METRIC_GEOGRAPHIC>
-            <<<grid, VT, 0, stream>>>(x, y, z, n, n_blocks, part, n_parts, nlags, edges, sum_d, sum_g, count);
+        variogram_bins_kernel<CMX_METRIC_GEOGRAPHIC><<<grid, VT, 0, stream>>>(x, y, z, n, n_blocks, part, n_parts, nlags, edges,
+                                                                           sum_d, sum_g, count, part_d, part_g, part_c);
     note_launch();
+    if (part_d) {
+        variogram_reduce_kernel<<<1, MAX_LAGS, 0, stream>>>(part_d, part_g, part_c, grid, nlags, sum_d, sum_g, count);
+        note_launch();
+    }
     return check_launch();
 }
 

@@ -22,6 +22,8 @@ __all__ = [
     "idw",
     "idw_apply",
     "empirical_variogram",
+    "variogram_fit_device",
+    "fit_variogram_native",
     "ok_moving_window",
     "knn3",
     "ok_solve",
@@ -145,15 +147,17 @@ def get_search() -> str:
     return _search
 
 
-def _options(search: str | None = None, peer_out: tuple | None = None):
-    """``cmx_options`` for one call: search algorithm (None -> the process default) and, optionally, the
-    peer buffers ``(pointers, m_total, m_offset)`` the batched IDW kernels store into."""
+def _options(search: str | None = None, peer_out: tuple | None = None, params_on_device: bool = False):
+    """``cmx_options`` for one call: search algorithm (None -> the process default), optionally the
+    peer buffers ``(pointers, m_total, m_offset)`` the batched IDW kernels store into, and whether the kriging
+    entry points find their variogram parameters in device memory."""
     search = _search if search is None else search
     if search not in SEARCH_ALGORITHMS:
         raise ValueError(f"unknown search algorithm {search!r}; choose from {sorted(SEARCH_ALGORITHMS)}")
     opt = _lib.Options()
     opt.search = SEARCH_ALGORITHMS[search]
     opt.n_peers = 0
+    opt.params_on_device = int(bool(params_on_device))
     if peer_out is not None:
         ptrs, m_total, m_off = peer_out
         if not 1 <= len(ptrs) <= _lib.MAX_PEERS:
@@ -392,8 +396,10 @@ def empirical_variogram(x, y, z, nlags: int, *, geographic: bool = False, group=
         edges_t = torch.tensor(edges, dtype=torch.float64, device=dev)
         sums = torch.zeros((2, nlags), dtype=torch.float64, device=dev)
         count = torch.zeros(nlags, dtype=torch.int64, device=dev)
+        ws = _workspace(lib.cmx_variogram_workspace_bytes(nlags), dev)  # deterministic two-stage reduction
         _lib.check(lib.cmx_variogram_bins(_ptr(x), _ptr(y), _ptr(z), n, metric, part, n_parts, nlags, _ptr(edges_t),
-                                          _ptr(sums[0]), _ptr(sums[1]), _ptr(count), _stream()), "cmx_variogram_bins")
+                                          _ptr(sums[0]), _ptr(sums[1]), _ptr(count), _ptr(ws), ws.numel(), _stream()),
+                   "cmx_variogram_bins")
         if dist is not None:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
             dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
@@ -404,6 +410,87 @@ def empirical_variogram(x, y, z, nlags: int, *, geographic: bool = False, group=
     semivariance = sums_h[1][good] / count_h[good]
     raw = dict(dmin=dmin, dmax=dmax, edges=np.array(edges), sum_d=sums_h[0], sum_g=sums_h[1], count=count_h)
     return lags, semivariance, raw
+
+
+def _variogram_params(params, dev):
+    """``(pointer argument, on_device, keep-alive)``: a CUDA tensor of 3 doubles is passed as it is (no host round
+    trip: e.g. the output of ``variogram_fit_device``), anything else as a host array of 3 doubles."""
+    if isinstance(params, torch.Tensor) and params.device.type == "cuda":
+        pt = params.to(device=dev, dtype=torch.float64).contiguous()
+        if pt.numel() < 3:
+            raise ValueError("device-resident variogram parameters must hold 3 doubles")
+        return _ptr(pt), True, pt
+    vals = [float(v) for v in (params.tolist() if hasattr(params, "tolist") else list(params))]
+    arr = (ctypes.c_double * 3)(*(vals + [0.0] * (3 - len(vals))))
+    return ctypes.cast(arr, ctypes.c_void_p), False, arr
+
+
+def fit_variogram_native(lags, semivariance, variogram_model: str):
+    """pykrige ``_calculate_variogram_model`` on the host, natively: the restated SciPy TRF iteration of
+    ``csrc/variogram_fit.cuh`` (``cmx_variogram_fit_host``; ~50 us instead of ~4 ms of ``scipy.optimize``).
+    Returns the parameter array (2 entries for "linear", else 3)."""
+    lib = _lib.load()
+    lags = np.ascontiguousarray(lags, dtype=np.float64)
+    sv = np.ascontiguousarray(semivariance, dtype=np.float64)
+    if lags.ndim != 1 or lags.shape != sv.shape or not 1 <= lags.size <= 64:
+        raise ValueError("lags and semivariance must be one-dimensional arrays of the same length (1..64)")
+    out = (ctypes.c_double * 3)()
+    rc = lib.cmx_variogram_fit_host(_lib.VARIOGRAM_MODELS[variogram_model], lags.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                    sv.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), int(lags.size), out, None)
+    if rc < 0:
+        _lib.check(rc, "cmx_variogram_fit_host")
+    return np.array(out[: 2 if variogram_model == "linear" else 3])
+
+
+def variogram_fit_device(x, y, z, nlags: int, variogram_model: str, *, geographic: bool = False, group=None):
+    """Empirical variogram AND its model fit entirely on the device, without a host round trip:
+    pair min/max (K3) -> bin edges -> bin sums (K3) -> TRF fit (one thread), all on the current stream.
+
+    Returns a dict of device tensors: ``params`` (3 doubles; feed it to ``ok_moving_window`` / ``ok_solve``),
+    ``lags`` / ``semivariance`` ([nlags], the ``info[1]`` used entries first), ``info`` = (status, points, function
+    evaluations), ``minmax``, ``sums`` ([2, nlags]) and ``count``.  Reference: pykrige ``OrdinaryKriging.__init__``
+    reached from kriging.py:215-224.  ``group``: shard the pair set over the ranks (all-reduce of 2 + 3 nlags numbers).
+    """
+    lib = _lib.load()
+    dev = _require_cuda(x.device if isinstance(x, torch.Tensor) else None)
+    x, y, z = _as_f64(x, dev), _as_f64(y, dev), _as_f64(z, dev)
+    n, nlags = x.numel(), int(nlags)
+    if nlags > 64:
+        raise NotImplementedError("nlags above 64 is not supported by the variogram kernel (climatrix's range is 4..20)")
+    metric = _lib.METRIC_GEOGRAPHIC if geographic else _lib.METRIC_EUCLIDEAN
+    part, n_parts, dist = 0, 1, None
+    if group is not None:
+        import torch.distributed as dist
+
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            part, n_parts = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            dist = None
+    with torch.cuda.device(dev):
+        mm = torch.empty(2, dtype=torch.float64, device=dev)
+        _lib.check(lib.cmx_variogram_minmax(_ptr(x), _ptr(y), n, metric, part, n_parts, _ptr(mm), _stream()), "cmx_variogram_minmax")
+        if dist is not None:
+            mm[0].neg_()
+            dist.all_reduce(mm, op=dist.ReduceOp.MAX, group=group)
+            mm[0].neg_()
+        edges = torch.empty(nlags + 1, dtype=torch.float64, device=dev)
+        _lib.check(lib.cmx_variogram_edges(_ptr(mm), nlags, _ptr(edges), _stream()), "cmx_variogram_edges")
+        sums = torch.zeros((2, nlags), dtype=torch.float64, device=dev)
+        count = torch.zeros(nlags, dtype=torch.int64, device=dev)
+        ws = _workspace(lib.cmx_variogram_workspace_bytes(nlags), dev)
+        _lib.check(lib.cmx_variogram_bins(_ptr(x), _ptr(y), _ptr(z), n, metric, part, n_parts, nlags, _ptr(edges),
+                                          _ptr(sums[0]), _ptr(sums[1]), _ptr(count), _ptr(ws), ws.numel(), _stream()),
+                   "cmx_variogram_bins")
+        if dist is not None:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
+        params = torch.zeros(3, dtype=torch.float64, device=dev)
+        lags = torch.empty(nlags, dtype=torch.float64, device=dev)
+        sv = torch.empty(nlags, dtype=torch.float64, device=dev)
+        info = torch.zeros(3, dtype=torch.int32, device=dev)
+        _lib.check(lib.cmx_variogram_fit(_lib.VARIOGRAM_MODELS[variogram_model], nlags, _ptr(sums[0]), _ptr(sums[1]), _ptr(count),
+                                         _ptr(params), _ptr(lags), _ptr(sv), _ptr(info), _stream()), "cmx_variogram_fit")
+    return dict(params=params, lags=lags, semivariance=sv, info=info, minmax=mm, edges=edges, sums=sums, count=count)
 
 
 def ok_moving_window(s_x, s_y, z, t_x, t_y, grid: bool, *, k: int, variogram_model: str, params,
@@ -417,8 +504,9 @@ def ok_moving_window(s_x, s_y, z, t_x, t_y, grid: bool, *, k: int, variogram_mod
     (and the variance) is stored in; the standardised values ``z`` and all arithmetic are float64.
     """
     lib = _lib.load()
-    opt = _options(search)
     dev = _require_cuda(s_x.device if isinstance(s_x, torch.Tensor) else None)
+    p, on_device, _keep = _variogram_params(params, dev)
+    opt = _options(search, params_on_device=on_device)
     s_x, s_y = _as_f64(s_x, dev), _as_f64(s_y, dev)
     t_x, t_y = _as_f64(t_x, dev), _as_f64(t_y, dev)
     if not isinstance(z, torch.Tensor):
@@ -429,7 +517,6 @@ def ok_moving_window(s_x, s_y, z, t_x, t_y, grid: bool, *, k: int, variogram_mod
     if not grid and t_x.numel() != t_y.numel():
         raise ValueError("xpoints and ypoints must have same dimensions when treated as listing discrete points.")
     model = _lib.VARIOGRAM_MODELS[variogram_model]
-    p = (ctypes.c_double * 3)(*[float(v) for v in list(params) + [0.0] * (3 - len(params))])
     k = int(k)
     with torch.cuda.device(dev):
         out = torch.empty(m, dtype=dtype, device=dev)
@@ -482,7 +569,7 @@ def ok_solve(s_x, s_y, z, idx: torch.Tensor, d2: torch.Tensor, *, variogram_mode
         z = torch.as_tensor(np.ascontiguousarray(z))
     z = z.to(device=dev, dtype=torch.float64).contiguous()
     m, k = idx.shape
-    p = (ctypes.c_double * 3)(*[float(v) for v in list(params) + [0.0] * (3 - len(params))])
+    p, on_device, _keep = _variogram_params(params, dev)
     with torch.cuda.device(dev):
         out = torch.empty(m, dtype=dtype, device=dev)
         sig = torch.empty(m, dtype=dtype, device=dev) if return_sigmasq else None
@@ -492,7 +579,7 @@ def ok_solve(s_x, s_y, z, idx: torch.Tensor, d2: torch.Tensor, *, variogram_mode
         rc = fn(_ptr(s_x), _ptr(s_y), _ptr(z), s_x.numel(), _ptr(idx.contiguous()), _ptr(d2.contiguous()), m,
                 _lib.METRIC_GEOGRAPHIC if geographic else _lib.METRIC_EUCLIDEAN, k, _lib.VARIOGRAM_MODELS[variogram_model],
                 p, int(exact_values), float(out_scale), float(out_shift), _ptr(out), _ptr(sig), _ptr(nsing),
-                _ptr(ws), ws.numel() if ws is not None else 0, _stream())
+                _ptr(ws), ws.numel() if ws is not None else 0, _options(params_on_device=on_device), _stream())
     _lib.check(rc, "cmx_ok_solve")
     if return_sigmasq:
         return out, sig, nsing

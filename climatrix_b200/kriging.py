@@ -121,6 +121,10 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
     devices : list of devices          (new) moving window: shard the target rows over several GPUs of this process
     group : torch.distributed group    (new) moving window, one process per GPU (torchrun): pair-range-sharded
                                        variogram + all-reduce, row bands, NCCL all-gather; every rank returns the field
+    fit : "native" | "scipy"           (new) who runs pykrige's soft-L1 least-squares fit of the variogram model:
+                                       "native" (default) = the restated SciPy TRF iteration on the device, no host round
+                                       trip between the variogram and the solves; "scipy" = the very
+                                       ``scipy.optimize.least_squares`` call pykrige makes, on the host (~4 ms)
     """
 
     NAME: ClassVar[str] = "ok"
@@ -138,7 +142,7 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
                  anisotropy_scaling: float | None = None, coordinates_type: str | None = None,
                  variogram_model: str | None = None, pseudo_inv: bool = False, *,
                  n_closest_points: int | None = None, k: int | None = None, dtype="float64", device=None,
-                 devices=None, group=None, return_variance: bool = False):
+                 devices=None, group=None, return_variance: bool = False, fit: str = "native"):
         super().__init__(dataset, target_domain)
         extra = extra_dimensions(dataset.domain)
         if extra:
@@ -177,6 +181,9 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
         # pykrige's execute() also returns the kriging variance, which climatrix drops (kriging.py:236); with
         # return_variance=True the moving-window paths keep it in ``self.variance_`` (target shape, data units^2)
         self.return_variance = bool(return_variance)
+        if fit not in ("native", "scipy"):
+            raise ValueError("fit must be 'native' or 'scipy'")
+        self.fit = fit
         self.variance_ = None
         self.variogram_model_parameters = None
         self.lags = None
@@ -232,10 +239,18 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
             xs = torch.as_tensor(x_adj).to(dev)
             ys = torch.as_tensor(y_adj).to(dev)
             zs = torch.as_tensor(np.ascontiguousarray(z, dtype=np.float64)).to(dev)
-            lags, semivariance, _ = kernels.empirical_variogram(xs, ys, zs, self.nlags, geographic=geographic,
-                                                                group=self.group)
-            params = fit_variogram(lags, semivariance, self.variogram_model)
-            self.lags, self.semivariance, self.variogram_model_parameters = lags, semivariance, params
+            fit_dev = None
+            if self.fit == "scipy":
+                lags, semivariance, _ = kernels.empirical_variogram(xs, ys, zs, self.nlags, geographic=geographic,
+                                                                    group=self.group)
+                params = fit_variogram(lags, semivariance, self.variogram_model)
+                self.lags, self.semivariance, self.variogram_model_parameters = lags, semivariance, params
+            else:
+                # variogram + fit stay on the device; `params` is a device tensor the solves read directly and the
+                # host sees the fitted values only when it fetches the result
+                fit_dev = kernels.variogram_fit_device(xs, ys, zs, self.nlags, self.variogram_model, geographic=geographic,
+                                                       group=self.group)
+                params = fit_dev["params"]
 
             # --- targets: own min/max normalisation (kriging.py:230-235), then pykrige execute (A.2) ---
             t_lat = _minmax_scale(tgt.latitude.values)
@@ -305,8 +320,13 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
                     )
             else:
                 sig = None
+                if fit_dev is not None:
+                    params = self._collect_fit(fit_dev)
+                    fit_dev = None
                 values = self._global(torch, dev, xs, ys, zs, xpts, ypts, sparse_target, xc, yc, scaling, params,
                                       geographic, v_mean, v_std, tdtype)
+            if fit_dev is not None:
+                self._collect_fit(fit_dev)
             if self.return_variance and sig is not None:
                 # sigma^2 comes out in standardised units (values were z-scored): back to data units^2
                 shape = (ypts.size, xpts.size) if not sparse_target else (xpts.size,)
@@ -318,6 +338,18 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
         return type(self.dataset)(tgt.to_xarray(values, getattr(self.dataset.da, "name", None)))
 
     # ------------------------------------------------------------------ #
+    def _collect_fit(self, fit_dev):
+        """Fetch what the device-side variogram + fit produced (pykrige keeps them as attributes of the model)."""
+        status, points, _nfev = (int(v) for v in fit_dev["info"].cpu())
+        if status < 0 or points < 1:
+            raise ValueError("the variogram model could not be fitted (no pairs, or degenerate semivariances: "
+                             "scipy.optimize.least_squares raises for the same inputs)")
+        params = fit_dev["params"].cpu().numpy()[: 2 if self.variogram_model == "linear" else 3].copy()
+        self.lags = fit_dev["lags"].cpu().numpy()[:points].copy()
+        self.semivariance = fit_dev["semivariance"].cpu().numpy()[:points].copy()
+        self.variogram_model_parameters = params
+        return params
+
     def _gamma_t(self, torch, params, d):
         model = self.variogram_model
         p = [float(v) for v in params]

@@ -84,6 +84,8 @@ extern "C" {
  * at this call's first target m_offset.  The call's own `out` argument is then unused (but must be non-null).
  * n_peers = 0: plain output.  Synchronising the ranks before the buffers are read is the caller's job.
  * A redirected call with n_batch == 1 returns CMX_ERR_UNSUPPORTED.
+ *
+ * params_on_device: see the kriging entry points.
  */
 #define CMX_SEARCH_AUTO 0
 #define CMX_SEARCH_BRUTE 1
@@ -94,6 +96,8 @@ typedef struct cmx_options {
     void* peer_out[CMX_MAX_PEERS];
     int64_t m_total;
     int64_t m_offset;
+    int params_on_device; /* cmx_ok_mw_* / cmx_ok_solve_*: `params` is a DEVICE pointer to 3 doubles (e.g. written by
+                             cmx_variogram_fit on the same stream) instead of a host array: no host round trip */
 } cmx_options;
 
 /* variogram models, pykrige/variogram_models.py (params: see cmx_ok_mw_*) */
@@ -192,10 +196,36 @@ int cmx_variogram_minmax(const double* x, const double* y, int64_t n, int metric
  * edges[nlags+1] (device): bin n holds pairs with edges[n] <= d < edges[n+1].
  * sum_d / sum_g / count [nlags] (device) are ACCUMULATED into (zero them first);
  * g = 0.5 * (z_i - z_j)^2.  nlags <= 64 (CMX_ERR_UNSUPPORTED above; climatrix's hyper-parameter range is 4..20).
+ * workspace: cmx_variogram_workspace_bytes(nlags) bytes of scratch make the reduction deterministic (per-CTA partial
+ * sums combined in a fixed order: reproducible fits); NULL -> floating-point atomics (sums vary in the last bits
+ * from run to run).
  */
+size_t cmx_variogram_workspace_bytes(int nlags);
 int cmx_variogram_bins(const double* x, const double* y, const double* z, int64_t n, int metric, int part,
                        int n_parts, int nlags, const double* edges,
-                       double* sum_d, double* sum_g, unsigned long long* count, void* stream);
+                       double* sum_d, double* sum_g, unsigned long long* count,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Variogram-model fit = pykrige core._calculate_variogram_model (weight=False):
+ * scipy.optimize.least_squares(residuals, x0, bounds, loss="soft_l1") with pykrige's start point and bounds, i.e. the
+ * point where SciPy's Trust Region Reflective iteration stops at its default tolerances (which is what the reference
+ * obtains; it is not the exact minimiser).  The iteration is restated in csrc/variogram_fit.cuh.
+ *  cmx_variogram_fit_host: plain host function (no device): n <= 64 (lag, semivariance) points -> params_out[3]
+ *                          (linear: slope, nugget, 0).  Returns the termination status (1 gtol, 2 ftol, 3 xtol, 4 both,
+ *                          0 evaluation budget spent) or a negative CMX_ERR_*.
+ *  cmx_variogram_edges:    bin edges on the device from the device-resident minmax, with pykrige's arithmetic.
+ *  cmx_variogram_fit:      the same fit on the device from the accumulated bins (empty bins dropped, as pykrige does):
+ *                          params_out[3]; optional lags_out / semivariance_out [nlags] (used entries first) and
+ *                          info[3] = {status, points, function evaluations}.  No host round trip between the variogram
+ *                          and the kriging solves (cmx_options.params_on_device).
+ */
+int cmx_variogram_fit_host(int variogram_model, const double* lags, const double* semivariance, int n, double params_out[3],
+                           int* nfev_out);
+int cmx_variogram_edges(const double* minmax, int nlags, double* edges, void* stream);
+int cmx_variogram_fit(int variogram_model, int nlags, const double* sum_d, const double* sum_g,
+                      const unsigned long long* count, double* params_out, double* lags_out, double* semivariance_out,
+                      int32_t* info, void* stream);
 
 /* ---- ordinary kriging, moving window ---- */
 
@@ -252,13 +282,13 @@ int cmx_ok_solve_f64(const double* s_x, const double* s_y, const double* z, int6
                      int variogram_model, const double params[3], int exact_values,
                      double out_scale, double out_shift,
                      double* out, double* sigmasq_out, int32_t* n_singular,
-                     void* workspace, size_t workspace_bytes, void* stream);
+                     void* workspace, size_t workspace_bytes, const cmx_options* options, void* stream);
 int cmx_ok_solve_f32(const double* s_x, const double* s_y, const double* z, int64_t n_samples,
                      const int32_t* idx, const double* d2, int64_t n_targets, int metric, int k,
                      int variogram_model, const double params[3], int exact_values,
                      double out_scale, double out_shift,
                      float* out, float* sigmasq_out, int32_t* n_singular,
-                     void* workspace, size_t workspace_bytes, void* stream);
+                     void* workspace, size_t workspace_bytes, const cmx_options* options, void* stream);
 
 /* total scratch for cmx_ok_mw_* (includes the kNN scratch and cmx_ok_solve_workspace_bytes) */
 size_t cmx_ok_workspace_bytes(int k, int64_t n_targets);

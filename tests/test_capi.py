@@ -60,14 +60,15 @@ def test_argument_validation_returns_codes_without_a_device(lib):
     # sparse targets need matching lengths
     assert lib.cmx_knn(one, one, 1000, one, 4, one, 5, 0, 8, one, null, one, 1 << 40, None, null) == _lib.ERR_BAD_ARG
     # variogram: too many lags / unknown metric
-    assert lib.cmx_variogram_bins(one, one, one, 10, 0, 0, 1, 65, one, one, one, one, null) == _lib.ERR_UNSUPPORTED
+    assert lib.cmx_variogram_bins(one, one, one, 10, 0, 0, 1, 65, one, one, one, one, null, 0, null) == _lib.ERR_UNSUPPORTED
+    assert lib.cmx_variogram_workspace_bytes(6) > 0 and lib.cmx_variogram_workspace_bytes(65) == 0
     assert lib.cmx_variogram_minmax(one, one, 10, 7, 0, 1, one, null) == _lib.ERR_UNSUPPORTED
     assert lib.cmx_variogram_minmax(one, one, 10, 0, 2, 2, one, null) == _lib.ERR_BAD_ARG  # part must be < n_parts
-    p = (ctypes.c_double * 3)(1.0, 1.0, 0.0)
+    p = ctypes.cast((ctypes.c_double * 3)(1.0, 1.0, 0.0), ctypes.c_void_p)
     assert lib.cmx_ok_mw_f64(one, one, one, 10, one, 2, one, 2, 1, 0, 4, 9, p, 1, 1.0, 0.0, one, null, null, one, 1 << 40,
                              None, null) == _lib.ERR_UNSUPPORTED
     assert lib.cmx_ok_solve_f64(one, one, one, 10, one, one, 5, 0, 200, 0, p, 1, 1.0, 0.0, one, null, null, null, 0,
-                                null) == _lib.ERR_K_TOO_LARGE
+                                None, null) == _lib.ERR_K_TOO_LARGE
     assert lib.cmx_ok_solve_workspace_bytes(1000) >= 4000
 
 

@@ -607,3 +607,65 @@ def test_sparse_matching_like_comparison():
         diff, kept = sparse_difference(pv, pred_pts, tv, true_pts, thr)
         np.testing.assert_array_equal(kept, np.where(ok0)[0])
         np.testing.assert_array_equal(diff, (pv - tv[np.where(ok0, i0, 0)])[ok0])
+
+
+# ------------------------------------------------------------------------------------------
+# variogram fit on the device (restated SciPy TRF) and the run-to-run reproducibility of the variogram
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("model", ["linear", "power", "gaussian", "spherical", "exponential"])
+@pytest.mark.parametrize("nlags,geo", [(6, False), (12, False), (6, True)])
+def test_device_variogram_fit_matches_host_fit_and_scipy(model, nlags, geo):
+    from climatrix_b200.kriging import fit_variogram
+
+    rng = np.random.default_rng(nlags + len(model))
+    n = 2500
+    x, y = (rng.uniform(-170, 170, n), rng.uniform(-80, 80, n)) if geo else (rng.uniform(-1, 1, n), rng.uniform(-1, 1, n))
+    z = np.sin(0.03 * x if geo else 3 * x) + np.cos(0.05 * y if geo else 2 * y) + 0.3 * rng.normal(size=n)
+    fit = K.variogram_fit_device(x, y, z, nlags, model, geographic=geo)
+    lags, sv, raw = K.empirical_variogram(x, y, z, nlags, geographic=geo)
+    status, points, nfev = (int(v) for v in fit["info"].cpu())
+    assert status >= 0 and points == len(lags) and nfev >= 1
+    # same kernels, deterministic reduction: the device-resident path sees exactly the same variogram
+    np.testing.assert_array_equal(fit["lags"].cpu().numpy()[:points], lags)
+    np.testing.assert_array_equal(fit["semivariance"].cpu().numpy()[:points], sv)
+    np.testing.assert_array_equal(fit["edges"].cpu().numpy(), raw["edges"])
+    got = fit["params"].cpu().numpy()[: 2 if model == "linear" else 3]
+    host = K.fit_variogram_native(lags, sv, model)
+    np.testing.assert_allclose(got, host, rtol=1e-6, atol=1e-9)  # device libm / fma contraction: last-bit differences
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = fit_variogram(lags, sv, model)
+    np.testing.assert_allclose(got, ref, rtol=2e-6, atol=1e-8)
+
+
+def test_variogram_and_kriging_are_reproducible_from_run_to_run():
+    """Two-stage deterministic reduction in K3 (no floating-point atomics): identical sums, fits and fields."""
+    la, lo, v, _ = _samples(6000, 99)
+    src = static_sparse(la, lo, v)
+    tgt = cm.Domain.from_lat_lon(np.linspace(-80, 80, 41), np.linspace(-170, 170, 83))
+    kw = dict(n_closest_points=20, variogram_model="exponential", anisotropy_scaling=1.0)
+    a = cm.OrdinaryKrigingReconstructor(src, tgt, **kw)
+    fa = a.reconstruct().da.values
+    for _ in range(2):
+        b = cm.OrdinaryKrigingReconstructor(src, tgt, **kw)
+        fb = b.reconstruct().da.values
+        np.testing.assert_array_equal(b.variogram_model_parameters, a.variogram_model_parameters)
+        np.testing.assert_array_equal(b.semivariance, a.semivariance)
+        np.testing.assert_array_equal(fb, fa)
+
+
+@pytest.mark.parametrize("model", ["spherical", "linear", "gaussian"])
+def test_ok_reconstructor_native_fit_equals_scipy_fit(model):
+    la, lo, v, _ = _samples(3000, 123)
+    src = static_sparse(la, lo, v)
+    tgt = cm.Domain.from_lat_lon(np.linspace(-80, 80, 33), np.linspace(-170, 170, 65))
+    kw = dict(n_closest_points=16, variogram_model=model, anisotropy_scaling=1.0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = cm.OrdinaryKrigingReconstructor(src, tgt, fit="scipy", **kw)
+        fa = a.reconstruct().da.values
+    b = cm.OrdinaryKrigingReconstructor(src, tgt, fit="native", **kw)
+    fb = b.reconstruct().da.values
+    np.testing.assert_array_equal(b.lags, a.lags)
+    np.testing.assert_allclose(b.variogram_model_parameters, a.variogram_model_parameters, rtol=2e-6, atol=1e-8)
+    assert np.max(np.abs(fb - fa)) <= 1e-6 * np.max(np.abs(fa))
