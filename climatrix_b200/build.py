@@ -17,7 +17,11 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.environ.get("CMX_LIB") or os.path.join(LIB_DIR, "libclimatrix_b200.so")  # CMX_LIB: tuning variants
 SOURCES = ["capi.cu", "knn.cu", "knn3.cu", "idw.cu", "variogram.cu", "kriging.cu"]
-HEADERS = ["common.cuh", "rerank.cuh", "ok_chol.cuh", os.path.join("..", "..", "include", "climatrix_b200.h")]
+HEADERS = ["common.cuh", "rerank.cuh", "ok_chol.cuh", "variogram_fit.cuh", os.path.join("..", "..", "include", "climatrix_b200.h")]
+
+# variogram.cu holds the restated SciPy TRF fit: its stopping tests compare finite-difference noise with 1e-8, so the
+# device build must round like the host build (no multiply-add contraction) to stop at the same iterate
+EXTRA_FLAGS = {"variogram.cu": ["-fmad=false"]}
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -54,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *EXTRA_FLAGS.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
         return src, obj, subprocess.run(cmd, capture_output=True, text=True)
 
     objs = []

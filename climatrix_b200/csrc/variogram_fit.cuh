@@ -23,6 +23,9 @@
 
 #include <float.h>
 #include <math.h>
+#ifdef CMX_VFIT_TRACE
+#include <stdio.h>
+#endif
 
 #ifdef __CUDACC__
 #define CMX_HD __host__ __device__
@@ -534,7 +537,7 @@ CMX_HD inline int variogram_fit_trf(int model, int m, const double* lags, const 
             status = 1;
             terminated = true;
         }
-#if defined(CMX_VFIT_TRACE) && !defined(__CUDA_ARCH__)
+#if defined(CMX_VFIT_TRACE) && (!defined(__CUDA_ARCH__) || defined(CMX_VFIT_TRACE_DEVICE))
         printf("nfev %3d cost %.10e g_norm %.4e Delta %.6e alpha %.4e x = %.12e %.12e %.12e\n", nfev, cost, g_norm, Delta, alpha, x[0], x[1], n > 2 ? x[2] : 0.0);
 #endif
         if (terminated || nfev == max_nfev) break;

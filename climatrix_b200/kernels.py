@@ -382,19 +382,19 @@ def empirical_variogram(x, y, z, nlags: int, *, geographic: bool = False, group=
         else:
             dist = None
     with torch.cuda.device(dev):
-        mm = torch.empty(2, dtype=torch.float64, device=dev)
+        # one packed result [sum_d | sum_g | count | dmin dmax | edges] -> ONE device->host copy (one synchronisation)
+        packed = torch.zeros(3 * nlags + 2 + nlags + 1, dtype=torch.float64, device=dev)
+        sums = packed[: 2 * nlags].view(2, nlags)
+        mm = packed[3 * nlags: 3 * nlags + 2]
+        edges_t = packed[3 * nlags + 2:]
         _lib.check(lib.cmx_variogram_minmax(_ptr(x), _ptr(y), n, metric, part, n_parts, _ptr(mm), _stream()),
                    "cmx_variogram_minmax")
         if dist is not None:
             mm[0].neg_()  # one MAX all-reduce for (-min, max)
             dist.all_reduce(mm, op=dist.ReduceOp.MAX, group=group)
             mm[0].neg_()
-        dmin, dmax = (float(v) for v in mm.cpu())
-        # bin edges exactly as pykrige builds them (python floats): dmin + n*dd, last edge dmax + 0.001
-        dd = (dmax - dmin) / nlags
-        edges = [dmin + i * dd for i in range(nlags)] + [dmax + 0.001]
-        edges_t = torch.tensor(edges, dtype=torch.float64, device=dev)
-        sums = torch.zeros((2, nlags), dtype=torch.float64, device=dev)
+        # bin edges exactly as pykrige builds them: dmin + n*dd, last edge dmax + 0.001 (same IEEE operations, on the device)
+        _lib.check(lib.cmx_variogram_edges(_ptr(mm), nlags, _ptr(edges_t), _stream()), "cmx_variogram_edges")
         count = torch.zeros(nlags, dtype=torch.int64, device=dev)
         ws = _workspace(lib.cmx_variogram_workspace_bytes(nlags), dev)  # deterministic two-stage reduction
         _lib.check(lib.cmx_variogram_bins(_ptr(x), _ptr(y), _ptr(z), n, metric, part, n_parts, nlags, _ptr(edges_t),
@@ -403,8 +403,12 @@ def empirical_variogram(x, y, z, nlags: int, *, geographic: bool = False, group=
         if dist is not None:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
             dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
-        sums_h = sums.cpu().numpy()
-        count_h = count.cpu().numpy()
+        packed[2 * nlags: 3 * nlags] = count.to(torch.float64)  # pair counts < 2^53: exact
+        host = packed.cpu().numpy()
+    sums_h = host[: 2 * nlags].reshape(2, nlags)
+    count_h = host[2 * nlags: 3 * nlags].astype(np.int64)
+    dmin, dmax = float(host[3 * nlags]), float(host[3 * nlags + 1])
+    edges = host[3 * nlags + 2:].tolist()
     good = count_h > 0
     lags = sums_h[0][good] / count_h[good]
     semivariance = sums_h[1][good] / count_h[good]

@@ -121,10 +121,13 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
     devices : list of devices          (new) moving window: shard the target rows over several GPUs of this process
     group : torch.distributed group    (new) moving window, one process per GPU (torchrun): pair-range-sharded
                                        variogram + all-reduce, row bands, NCCL all-gather; every rank returns the field
-    fit : "native" | "scipy"           (new) who runs pykrige's soft-L1 least-squares fit of the variogram model:
-                                       "native" (default) = the restated SciPy TRF iteration on the device, no host round
-                                       trip between the variogram and the solves; "scipy" = the very
-                                       ``scipy.optimize.least_squares`` call pykrige makes, on the host (~4 ms)
+    fit : "native" | "device" | "scipy"  (new) who runs pykrige's soft-L1 least-squares fit of the variogram model.
+                                       "native" (default): the restated SciPy TRF iteration in C++ on the host (~50 us; stops
+                                       at the same iterate as SciPy: parameters equal to ~1e-7).  "device": the same code in a
+                                       CUDA kernel, no host round trip between the variogram and the solves; the device's
+                                       exp / pow differ from the host's in the last bit, which moves TRF's noise-level
+                                       stopping decisions: parameters within ~1e-4 of SciPy's (fields ~1e-6).  "scipy": the
+                                       very ``scipy.optimize.least_squares`` call pykrige makes (~4 ms)
     """
 
     NAME: ClassVar[str] = "ok"
@@ -181,8 +184,8 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
         # pykrige's execute() also returns the kriging variance, which climatrix drops (kriging.py:236); with
         # return_variance=True the moving-window paths keep it in ``self.variance_`` (target shape, data units^2)
         self.return_variance = bool(return_variance)
-        if fit not in ("native", "scipy"):
-            raise ValueError("fit must be 'native' or 'scipy'")
+        if fit not in ("native", "device", "scipy"):
+            raise ValueError("fit must be 'native', 'device' or 'scipy'")
         self.fit = fit
         self.variance_ = None
         self.variogram_model_parameters = None
@@ -240,10 +243,13 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
             ys = torch.as_tensor(y_adj).to(dev)
             zs = torch.as_tensor(np.ascontiguousarray(z, dtype=np.float64)).to(dev)
             fit_dev = None
-            if self.fit == "scipy":
+            if self.fit != "device":
                 lags, semivariance, _ = kernels.empirical_variogram(xs, ys, zs, self.nlags, geographic=geographic,
                                                                     group=self.group)
-                params = fit_variogram(lags, semivariance, self.variogram_model)
+                if lags.size == 0:
+                    raise ValueError("the empirical variogram is empty (fewer than two distinct samples)")
+                params = (fit_variogram if self.fit == "scipy" else kernels.fit_variogram_native)(
+                    lags, semivariance, self.variogram_model)
                 self.lags, self.semivariance, self.variogram_model_parameters = lags, semivariance, params
             else:
                 # variogram + fit stay on the device; `params` is a device tensor the solves read directly and the
