@@ -50,10 +50,11 @@ __global__ void __launch_bounds__(VT) variogram_minmax_kernel(const double* __re
                                                               const double* __restrict__ y, long long n,
                                                               long long n_blocks, long long part, long long n_parts,
                                                               double* minmax) {
-    __shared__ double sx[VT], sy[VT];
+    __shared__ double2 sxy[VT];
     __shared__ double red[2 * VT / 32];
     const int tid = threadIdx.x;
     double lo = __longlong_as_double(0x7ff0000000000000LL), hi = -lo;
+    double lo2 = lo, hi2 = hi;  // second pair of accumulators: two independent min / max chains
     // this call's share of the lower-triangle blocks: b = part (mod n_parts)
     for (long long b = part + n_parts * blockIdx.x; b < n_blocks; b += n_parts * gridDim.x) {
         int bi, bj;
@@ -61,22 +62,32 @@ __global__ void __launch_bounds__(VT) variogram_minmax_kernel(const double* __re
         const long long i = (long long)bi * VT + tid;
         const long long j0 = (long long)bj * VT;
         __syncthreads();
-        if (j0 + tid < n) {
-            sx[tid] = x[j0 + tid];
-            sy[tid] = y[j0 + tid];
-        }
+        if (j0 + tid < n) sxy[tid] = make_double2(x[j0 + tid], y[j0 + tid]);
         __syncthreads();
         if (i < n) {
             const double xi = x[i], yi = y[i];
             const int jn = (int)((n - j0) < VT ? (n - j0) : VT);
             const int jend = bi == bj ? (tid < jn ? tid : jn) : jn;  // strictly lower triangle: j < i
-            for (int j = 0; j < jend; ++j) {
-                const double key = pair_key<METRIC>(xi, yi, sx[j], sy[j]);
-                lo = fmin(lo, key);
-                hi = fmax(hi, key);
+            int j = 0;
+#pragma unroll 4
+            for (; j + 1 < jend; j += 2) {
+                const double2 p0 = sxy[j], p1 = sxy[j + 1];
+                const double k0 = pair_key<METRIC>(xi, yi, p0.x, p0.y), k1 = pair_key<METRIC>(xi, yi, p1.x, p1.y);
+                lo = fmin(lo, k0);
+                hi = fmax(hi, k0);
+                lo2 = fmin(lo2, k1);
+                hi2 = fmax(hi2, k1);
+            }
+            if (j < jend) {
+                const double2 p0 = sxy[j];
+                const double k0 = pair_key<METRIC>(xi, yi, p0.x, p0.y);
+                lo = fmin(lo, k0);
+                hi = fmax(hi, k0);
             }
         }
     }
+    lo = fmin(lo, lo2);
+    hi = fmax(hi, hi2);
     lo = warp_min(lo);
     hi = warp_max(hi);
     if ((tid & 31) == 0) {
@@ -98,7 +109,25 @@ __global__ void __launch_bounds__(VT) variogram_minmax_kernel(const double* __re
     }
 }
 
-template <int METRIC>
+// Bin index of distance d: the bins are uniform except the last one (edge dmax + 0.001), so a multiply gives a guess that
+// is off by at most one; one comparison against the two edges of the guessed bin corrects it.  Every pair lies in
+// exactly one bin (edges[0] = dmin, edges[nlags] > dmax); `in` only filters NaN distances.
+__device__ __forceinline__ int variogram_bin(double d, double e0, double e_last, double inv_dd, int nlags,
+                                             const double* __restrict__ s_edges, bool& in) {
+    int b = (int)((d - e0) * inv_dd);
+    b = b < 0 ? 0 : (b > nlags - 1 ? nlags - 1 : b);
+    const double lo = s_edges[b], hi = s_edges[b + 1];
+    b += (d >= hi) - (d < lo);
+    b = b < 0 ? 0 : (b > nlags - 1 ? nlags - 1 : b);
+    in = d >= e0 && d < e_last;
+    return b;
+}
+
+// NL = 8 / 16 / 32: the per-thread accumulators are REGISTERS, updated by predicated adds (bin == q), so the pair loop has no
+// memory traffic besides the broadcast loads of the column sample - the generic version (NL = MAX_LAGS) keeps them in
+// (L1-resident) local memory and is bound by those dependent load-add-store chains (ncu: long_scoreboard 18 stalls per
+// issue, 106 instructions per pair).
+template <int METRIC, int NL>
 __global__ void __launch_bounds__(VT) variogram_bins_kernel(const double* __restrict__ x,
                                                             const double* __restrict__ y,
                                                             const double* __restrict__ z, long long n,
@@ -107,21 +136,23 @@ __global__ void __launch_bounds__(VT) variogram_bins_kernel(const double* __rest
                                                             double* sum_g, unsigned long long* count,
                                                             double* __restrict__ part_d, double* __restrict__ part_g,
                                                             unsigned long long* __restrict__ part_c) {
-    __shared__ double sx[VT], sy[VT], sz[VT];
-    __shared__ double s_edges[MAX_LAGS + 1];
-    __shared__ double s_wd[VT / 32][MAX_LAGS], s_wg[VT / 32][MAX_LAGS];
-    __shared__ unsigned s_wc[VT / 32][MAX_LAGS];
+    __shared__ double2 sxy[VT];
+    __shared__ double sz[VT];
+    __shared__ double s_edges[MAX_LAGS + 2];
+    __shared__ double s_wd[VT / 32][NL], s_wg[VT / 32][NL];
+    __shared__ unsigned s_wc[VT / 32][NL];
     const int tid = threadIdx.x;
     if (tid <= nlags) s_edges[tid] = edges[tid];
-    double acc_d[MAX_LAGS], acc_g[MAX_LAGS];
-    unsigned acc_c[MAX_LAGS];
-    for (int b = 0; b < nlags; ++b) {
+    double acc_d[NL], acc_g[NL];
+    unsigned acc_c[NL];
+#pragma unroll
+    for (int b = 0; b < NL; ++b) {
         acc_d[b] = 0.0;
         acc_g[b] = 0.0;
         acc_c[b] = 0u;
     }
     __syncthreads();
-    const double e0 = s_edges[0];
+    const double e0 = s_edges[0], e_last = s_edges[nlags];
     const double inv_dd = nlags > 0 && s_edges[1] > e0 ? 1.0 / (s_edges[1] - e0) : 0.0;
 
     for (long long blk = part + n_parts * blockIdx.x; blk < n_blocks; blk += n_parts * gridDim.x) {
@@ -131,8 +162,7 @@ __global__ void __launch_bounds__(VT) variogram_bins_kernel(const double* __rest
         const long long j0 = (long long)bj * VT;
         __syncthreads();
         if (j0 + tid < n) {
-            sx[tid] = x[j0 + tid];
-            sy[tid] = y[j0 + tid];
+            sxy[tid] = make_double2(x[j0 + tid], y[j0 + tid]);
             sz[tid] = z[j0 + tid];
         }
         __syncthreads();
@@ -140,38 +170,49 @@ __global__ void __launch_bounds__(VT) variogram_bins_kernel(const double* __rest
             const double xi = x[i], yi = y[i], zi = z[i];
             const int jn = (int)((n - j0) < VT ? (n - j0) : VT);
             const int jend = bi == bj ? (tid < jn ? tid : jn) : jn;
+#pragma unroll 2
             for (int j = 0; j < jend; ++j) {
-                double d = pair_key<METRIC>(xi, yi, sx[j], sy[j]);
+                const double2 pj = sxy[j];
+                double d = pair_key<METRIC>(xi, yi, pj.x, pj.y);
                 if (METRIC == CMX_METRIC_EUCLIDEAN) d = sqrt(d);
-                // bin: edges[b] <= d < edges[b+1]; uniform guess, then exact fix-up against the edges
-                int b = (int)((d - e0) * inv_dd);
-                b = b < 0 ? 0 : (b > nlags - 1 ? nlags - 1 : b);
-                while (b > 0 && d < s_edges[b]) --b;
-                while (b < nlags - 1 && d >= s_edges[b + 1]) ++b;
-                if (d >= s_edges[b] && d < s_edges[b + 1]) {
-                    const double dz = zi - sz[j];
+                bool in;
+                const int b = variogram_bin(d, e0, e_last, inv_dd, nlags, s_edges, in);
+                const double dz = zi - sz[j];
+                const double g = 0.5 * (dz * dz);
+                if (NL <= 32) {
+#pragma unroll
+                    for (int q = 0; q < NL; ++q) {
+                        if (in && b == q) {
+                            acc_d[q] += d;
+                            acc_g[q] += g;
+                            acc_c[q] += 1u;
+                        }
+                    }
+                } else if (in) {
                     acc_d[b] += d;
-                    acc_g[b] += 0.5 * (dz * dz);
+                    acc_g[b] += g;
                     acc_c[b] += 1u;
                 }
             }
-            // (32-bit per-thread counters: a thread sees at most n_blocks / gridDim.x * 256 < 2^32 pairs for n < 2^31)
         }
     }
     // Deterministic reduction: lanes by shuffles, the warps of the CTA in warp order, the CTAs (whose share of the pair
     // blocks is fixed by the launch geometry) in CTA order by variogram_reduce_kernel - no floating-point atomics, so
     // the sums, the fitted parameters and the kriged field are reproducible from run to run.  Without scratch
-    // (part_d == nullptr) the CTA results are accumulated with atomics as before.
-    for (int b = 0; b < nlags; ++b) {
-        const double d = warp_sum(acc_d[b]);
-        const double g = warp_sum(acc_g[b]);
-        unsigned c = acc_c[b];
+    // (part_d == nullptr) the CTA results are accumulated with atomics.
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
-        if ((tid & 31) == 0) {
-            s_wd[tid >> 5][b] = d;
-            s_wg[tid >> 5][b] = g;
-            s_wc[tid >> 5][b] = c;
+    for (int b = 0; b < NL; ++b) {
+        if (b < nlags) {
+            const double d = warp_sum(acc_d[b]);
+            const double g = warp_sum(acc_g[b]);
+            unsigned c = acc_c[b];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
+            if ((tid & 31) == 0) {
+                s_wd[tid >> 5][b] = d;
+                s_wg[tid >> 5][b] = g;
+                s_wc[tid >> 5][b] = c;
+            }
         }
     }
     __syncthreads();
@@ -195,22 +236,29 @@ __global__ void __launch_bounds__(VT) variogram_bins_kernel(const double* __rest
     }
 }
 
-// sums the per-CTA partial results in CTA order and ADDS them to the outputs (one thread per bin)
+// sums the per-CTA partial results in a fixed order and ADDS them to the outputs: one warp per bin, lane l takes the
+// CTAs l, l + 32, ... in order, then a shuffle tree (the same tree every run: deterministic)
 __global__ void variogram_reduce_kernel(const double* __restrict__ part_d, const double* __restrict__ part_g,
                                         const unsigned long long* __restrict__ part_c, int n_ctas, int nlags, double* sum_d,
                                         double* sum_g, unsigned long long* count) {
-    const int b = threadIdx.x;
+    const int b = blockIdx.x, lane = threadIdx.x;
     if (b >= nlags) return;
     double d = 0.0, g = 0.0;
     unsigned long long c = 0ull;
-    for (int i = 0; i < n_ctas; ++i) {
+    for (int i = lane; i < n_ctas; i += 32) {
         d += part_d[(size_t)i * nlags + b];
         g += part_g[(size_t)i * nlags + b];
         c += part_c[(size_t)i * nlags + b];
     }
-    sum_d[b] += d;
-    sum_g[b] += g;
-    count[b] += c;
+    d = warp_sum(d);
+    g = warp_sum(g);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
+    if (lane == 0) {
+        sum_d[b] += d;
+        sum_g[b] += g;
+        count[b] += c;
+    }
 }
 
 // bin edges exactly as pykrige builds them: dmin + i * dd for i < nlags, last edge dmax + 0.001
@@ -334,15 +382,24 @@ int cmx_variogram_bins(const double* x, const double* y, const double* z, int64_
         part_g = part_d + (size_t)grid * nlags;
         part_c = reinterpret_cast<unsigned long long*>(part_g + (size_t)grid * nlags);
     }
-    if (metric == CMX_METRIC_EUCLIDEAN)
-        variogram_bins_kernel<CMX_METRIC_EUCLIDEAN><<<grid, VT, 0, stream>>>(x, y, z, n, n_blocks, part, n_parts, nlags, edges,
-                                                                          sum_d, sum_g, count, part_d, part_g, part_c);
-    else
-        variogram_bins_kernel<CMX_METRIC_GEOGRAPHIC><<<grid, VT, 0, stream>>>(x, y, z, n, n_blocks, part, n_parts, nlags, edges,
-                                                                           sum_d, sum_g, count, part_d, part_g, part_c);
+#define CMX_BINS_LAUNCH(METRIC, NL)                                                                                   \
+    variogram_bins_kernel<METRIC, NL><<<grid, VT, 0, stream>>>(x, y, z, n, n_blocks, part, n_parts, nlags, edges, sum_d, \
+                                                               sum_g, count, part_d, part_g, part_c)
+    if (metric == CMX_METRIC_EUCLIDEAN) {
+        if (nlags <= 8) CMX_BINS_LAUNCH(CMX_METRIC_EUCLIDEAN, 8);
+        else if (nlags <= 16) CMX_BINS_LAUNCH(CMX_METRIC_EUCLIDEAN, 16);
+        else if (nlags <= 32) CMX_BINS_LAUNCH(CMX_METRIC_EUCLIDEAN, 32);
+        else CMX_BINS_LAUNCH(CMX_METRIC_EUCLIDEAN, MAX_LAGS);
+    } else {
+        if (nlags <= 8) CMX_BINS_LAUNCH(CMX_METRIC_GEOGRAPHIC, 8);
+        else if (nlags <= 16) CMX_BINS_LAUNCH(CMX_METRIC_GEOGRAPHIC, 16);
+        else if (nlags <= 32) CMX_BINS_LAUNCH(CMX_METRIC_GEOGRAPHIC, 32);
+        else CMX_BINS_LAUNCH(CMX_METRIC_GEOGRAPHIC, MAX_LAGS);
+    }
+#undef CMX_BINS_LAUNCH
     note_launch();
     if (part_d) {
-        variogram_reduce_kernel<<<1, MAX_LAGS, 0, stream>>>(part_d, part_g, part_c, grid, nlags, sum_d, sum_g, count);
+        variogram_reduce_kernel<<<nlags, 32, 0, stream>>>(part_d, part_g, part_c, grid, nlags, sum_d, sum_g, count);
         note_launch();
     }
     return check_launch();
