@@ -55,6 +55,10 @@ struct KnnJob {
     double* d2_out;    // [M][k]  exact squared distance
     // fused IDW epilogue (idw.py:163-180); mode 0 = off
     int idw_mode;      // 1: single slice -> out[M] (weights + weighted mean in the kernel's epilogue)
+                       // 2: short batch, fused (binned search only): vals [N][n_batch] sample-major -> peers / out [n_batch][m_total]
+    long long n_batch;          // mode 2
+    const int* nonfinite_flag;  // mode 2: device flag, != 0 when some value is NaN / inf (null: test every value)
+    PeerOut peers;              // mode 2: where the [n_batch][m_total] result goes (n >= 1)
     int value_is_f32;  // dtype of vals/out
     const void* vals;  // [N] (mode 1)
     void* out;         // [M] (mode 1)

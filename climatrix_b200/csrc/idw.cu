@@ -575,7 +575,7 @@ int idw_entry(const double* s_lat, const double* s_lon, int64_t n, const V* vals
         job.out = out;
         return run_knn(job, stream);
     }
-    // batch: neighbour table once, then the HBM-bound batched apply.  Workspace: [tables | kNN scratch]
+    // batch.  Workspace: [tables | kNN scratch]
     if (k < 1 || k > CMX_MAX_K) return k < 1 ? CMX_ERR_BAD_ARG : CMX_ERR_K_TOO_LARGE;
     const size_t extra_bytes = (cmx_idw_workspace_bytes(k, M, n_batch) + 255) & ~size_t(255);
     if (!workspace || workspace_bytes < knn_ws + extra_bytes + 256) return CMX_ERR_WORKSPACE;
@@ -584,15 +584,41 @@ int idw_entry(const double* s_lat, const double* s_lon, int64_t n, const V* vals
     double* d2_tab = reinterpret_cast<double*>(extra);
     int* idx_tab = reinterpret_cast<int*>(extra + (size_t)M * k * sizeof(double));
     int* flag = reinterpret_cast<int*>(extra + (size_t)M * k * (sizeof(double) + sizeof(int)));
+    job.workspace = extra + extra_bytes;
+    job.workspace_bytes = workspace_bytes - (size_t)((extra + extra_bytes) - static_cast<unsigned char*>(workspace));
+
+#ifndef CMX_K2_UNION_MIN_BATCH
+#define CMX_K2_UNION_MIN_BATCH 128
+#endif
+    // Short batches with the cell-binned search: the weighting is applied inside the search kernel (fused batch
+    // epilogue, knn.cu finish_batch) - the [M][k] table is never written or read back.  Long batches amortise the table
+    // and use the neighbour-sharing K2 kernel; the brute-force kernel K1 keeps the table path.
+    if (search != CMX_SEARCH_BRUTE && layout == CMX_LAYOUT_SAMPLE_MAJOR && n_batch < CMX_K2_UNION_MIN_BATCH && M > 0) {
+        CMX_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), stream));
+        flag_nonfinite_kernel<V><<<sm_count() * 8, 256, 0, stream>>>(vals, (long long)n * n_batch, flag);
+        note_launch();
+        KnnJob fused = job;
+        fused.idw_mode = 2;
+        fused.vals = vals;
+        fused.n_batch = n_batch;
+        fused.nonfinite_flag = flag;
+        fused.peers = po;
+        if (po.n == 0) {  // plain output
+            fused.peers.base[0] = out;
+            fused.peers.n = 1;
+            fused.peers.m_total = M;
+            fused.peers.m_off = 0;
+        }
+        const int rc = run_knn(fused, stream);
+        if (rc != CMX_ERR_UNSUPPORTED) return rc;  // (unsupported: the binned search's scratch does not fit -> table path)
+    }
     job.idw_mode = 0;
     job.d2_out = d2_tab;
     if (!job.idx_out) job.idx_out = idx_tab;
-    job.workspace = extra + extra_bytes;
-    job.workspace_bytes = workspace_bytes - (size_t)((extra + extra_bytes) - static_cast<unsigned char*>(workspace));
     int rc = run_knn(job, stream);
     if (rc != CMX_OK) return rc;
-    return idw_from_table<V>(job.idx_out, d2_tab, 1, M, k, k, k_min, power, vals, n, n_batch, layout, out, flag,
-                             stream, po);
+    return idw_from_table<V>(job.idx_out, d2_tab, 1, M, k, k, k_min, power, vals, n, n_batch, layout, out, flag, stream,
+                             po);
 }
 
 template <typename V>

@@ -103,6 +103,7 @@ struct KnnArgs {
     double* bin_a;       // [N] sorted copies of the sample coordinates
     double* bin_b;
     int* bin_idx;        // [N] original sample index of each sorted slot
+    int chunk;           // K1c: consecutive work units (targets / four-target groups) a CTA takes at a time
 };
 
 // ------------------------------------------------------------------------------------------
@@ -360,10 +361,10 @@ __device__ __forceinline__ double finish_target(const KnnArgs& a, int lane, long
         // a slot still holding the (inf, INT_MAX) sentinel means fewer than k rankable samples were found
         // (NaN coordinates): it carries no weight and its index is never dereferenced
         const bool real = in && li[e] != INT_MAX;
-        w[e] = (real && a.j.idw_mode) ? idw_raw_weight(ld[e], a.j.power) : 0.0;
+        w[e] = (real && a.j.idw_mode == 1) ? idw_raw_weight(ld[e], a.j.power) : 0.0;
         wsum += w[e];
     }
-    if (!a.j.idw_mode) return 0.0;
+    if (a.j.idw_mode != 1) return 0.0;  // table only (mode 0), or the batch epilogue follows (mode 2)
     wsum = warp_sum(wsum);  // weights /= nansum(weights)            idw.py:165
     double num = 0.0, den = 0.0;
     int fin = 0;
@@ -387,6 +388,141 @@ __device__ __forceinline__ double finish_target(const KnnArgs& a, int lane, long
     for (int o = 16; o > 0; o >>= 1) fin += __shfl_xor_sync(kFull, fin, o);
     if (fin < a.j.k_min || den == 0.0) return quiet_nan<double>();  // idw.py:179-180
     return num / den;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused batch epilogue (idw_mode 2): the weighting of idw.py:163-180 applied to a short time / level batch right where
+// the neighbour list is final, so the [M][k] table is neither written nor read back (K2 does that for long batches).
+// The k (normalised weight, value-row offset) pairs of the target go to the warp's shared-memory strip; then the lanes
+// run along the batch axis: one 16-byte broadcast load per neighbour feeds P batch elements per lane, value rows are
+// read as contiguous segments (sample-major values).  Results stay in registers: r[p] is batch element p * 32 + lane.
+// ------------------------------------------------------------------------------------------
+struct __align__(16) BatchNbr {
+    double w;
+    unsigned long long off;  // byte offset of the neighbour's value row
+};
+
+template <int E, int P>
+__device__ __forceinline__ void finish_batch(const KnnArgs& a, int lane, const double (&ld)[E], const int (&li)[E],
+                                             BatchNbr* __restrict__ strip, double (&r)[P]) {
+    const int k = a.j.k;
+    const long long T = a.j.n_batch;
+    const size_t vsize = a.j.value_is_f32 ? 4 : 8;
+    double w[E], wsum = 0.0;
+    int real = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = e * 32 + lane;
+        const bool ok = i < k && li[e] != INT_MAX;  // (inf, INT_MAX): fewer than k rankable samples
+        w[e] = ok ? idw_raw_weight(ld[e], a.j.power) : 0.0;
+        wsum += w[e];
+        real += ok;
+    }
+    wsum = warp_sum(wsum);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) real += __shfl_xor_sync(kFull, real, o);
+    double den = 0.0;
+    __syncwarp();  // the strip may still be read by the previous target's sweep
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = e * 32 + lane;
+        const double wn = w[e] / wsum;  // weights /= nansum(weights)   idw.py:165
+        if (i < k) {
+            BatchNbr nb;
+            nb.w = wn;
+            nb.off = (unsigned long long)(li[e] != INT_MAX ? li[e] : 0) * (unsigned long long)T * vsize;
+            strip[i] = nb;
+        }
+        den += wn;
+    }
+    den = warp_sum(den);
+    __syncwarp();
+    const bool check = a.j.nonfinite_flag ? *a.j.nonfinite_flag != 0 : true;
+    const char* base[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const long long t = p * 32 + lane;
+        base[p] = static_cast<const char*>(a.j.vals) + (t < T ? t : 0) * (long long)vsize;
+    }
+    if (!check) {
+        double acc[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) acc[p] = 0.0;
+        if (a.j.value_is_f32) {
+#pragma unroll 8
+            for (int j = 0; j < k; ++j) {
+                const BatchNbr nb = strip[j];
+#pragma unroll
+                for (int p = 0; p < P; ++p) acc[p] = fma(nb.w, (double)*reinterpret_cast<const float*>(base[p] + nb.off), acc[p]);
+            }
+        } else {
+#pragma unroll 8
+            for (int j = 0; j < k; ++j) {
+                const BatchNbr nb = strip[j];
+#pragma unroll
+                for (int p = 0; p < P; ++p) acc[p] = fma(nb.w, *reinterpret_cast<const double*>(base[p] + nb.off), acc[p]);
+            }
+        }
+        // fewer than k_min existing neighbours -> NaN, like the single-slice epilogue (idw.py:179-180)
+        const double dn = real < a.j.k_min ? quiet_nan<double>() : den;
+#pragma unroll
+        for (int p = 0; p < P; ++p) r[p] = acc[p] / dn;
+    } else {  // some value is NaN / inf: weights[~isfinite] = 0; nansum; k_min counts finite values   idw.py:167-180
+        double num[P], dsum[P];
+        int fin[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) num[p] = dsum[p] = 0.0, fin[p] = 0;
+        for (int j = 0; j < k; ++j) {
+            const BatchNbr nb = strip[j];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const double v = a.j.value_is_f32 ? (double)*reinterpret_cast<const float*>(base[p] + nb.off)
+                                                  : *reinterpret_cast<const double*>(base[p] + nb.off);
+                if (isfinite(v) && nb.w > 0.0) {
+                    num[p] = fma(nb.w, v, num[p]);
+                    dsum[p] += nb.w;
+                    ++fin[p];
+                }
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < P; ++p) r[p] = (fin[p] < a.j.k_min || dsum[p] == 0.0) ? quiet_nan<double>() : num[p] / dsum[p];
+    }
+}
+
+// store G consecutive targets m0 .. m0 + G - 1 of every batch element this lane owns: one row segment per element
+template <int P, int G>
+__device__ __forceinline__ void store_batch(const KnnArgs& a, int lane, long long m0, int count, const double (&r)[G][P]) {
+    const PeerOut& po = a.j.peers;
+    const long long T = a.j.n_batch;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const long long t = p * 32 + lane;
+        if (t >= T) continue;
+        const long long at = t * po.m_total + po.m_off + m0;
+        for (int q = 0; q < po.n; ++q) {
+            if (a.j.value_is_f32) {
+                float* o = static_cast<float*>(po.base[q]) + at;
+                if (count == G && G == 4 && (reinterpret_cast<uintptr_t>(o) & 15u) == 0) {
+                    *reinterpret_cast<float4*>(o) = make_float4((float)r[0][p], (float)r[1][p], (float)r[2][p], (float)r[3][p]);
+                } else {
+#pragma unroll
+                    for (int g = 0; g < G; ++g)
+                        if (g < count) o[g] = (float)r[g][p];
+                }
+            } else {
+                double* o = static_cast<double*>(po.base[q]) + at;
+                if (count == G && G == 4 && (reinterpret_cast<uintptr_t>(o) & 15u) == 0) {
+                    *reinterpret_cast<double2*>(o) = make_double2(r[0][p], r[1][p]);
+                    *reinterpret_cast<double2*>(o + 2) = make_double2(r[2][p], r[3][p]);
+                } else {
+#pragma unroll
+                    for (int g = 0; g < G; ++g)
+                        if (g < count) o[g] = r[g][p];
+                }
+            }
+        }
+    }
 }
 
 // Warp-cooperative exact re-rank of one target's candidate buffer.
@@ -950,114 +1086,170 @@ __device__ __forceinline__ double seed_bound_d2_warp(const SeedGrid& s, const in
 // samples inside a cell (atomics in the scatter) cannot change the result: the list is the lexicographic
 // (d2, index) top-k of a candidate set that always contains the true top-k.
 template <int E>
+__device__ __forceinline__ void binned_search_target(const KnnArgs& a, const SeedGrid& s, const int* __restrict__ sat, int k,
+                                                     int lane, long long m, double (&ld)[E], int (&li)[E]) {
+    double ta, tb;
+    if (a.j.grid) {
+        const long long row = m / a.j.n_b;
+        ta = a.j.t_a[row];
+        tb = a.j.t_b[m - row * a.j.n_b];
+    } else {
+        ta = a.j.t_a[m];
+        tb = a.j.t_b[m];
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        ld[e] = CMX_INF;
+        li[e] = INT_MAX;
+    }
+    int ra0 = 0, ra1 = -1, cb0 = 0, cb1 = -1;
+    double kth = CMX_INF;
+    bool empty = true;
+    if (s.valid) {
+        kth = seed_bound_d2_warp(s, sat, ta, tb, k, lane);
+        if (kth < CMX_INF) {
+            const double D = sqrt(kth) * (1.0 + 1e-12);
+            ra0 = seed_cell(ta - D, s.a0, s.inv_h, s.ga);
+            ra1 = seed_cell(ta + D, s.a0, s.inv_h, s.ga);
+            cb0 = seed_cell(tb - D, s.b0, s.inv_h, s.gb);
+            cb1 = seed_cell(tb + D, s.b0, s.inv_h, s.gb);
+        } else {  // fewer than k finite samples (or a non-finite target): look at everything
+            ra1 = s.ga - 1;
+            cb1 = s.gb - 1;
+        }
+    }
+    const int R = ra1 - ra0 + 1;
+    for (int rb = 0; rb < R; rb += 32) {
+        int lo = 0, len = 0;
+        if (rb + lane < R) {
+            const int* S0 = sat + (size_t)(ra0 + rb + lane) * SAT_LD;
+            const int left = S0[SAT_LD + cb0] - S0[cb0];
+            lo = S0[s.gb] + left;
+            len = (S0[SAT_LD + cb1 + 1] - S0[cb1 + 1]) - left;
+        }
+        int pre = len;  // inclusive prefix sum of the segment lengths
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(kFull, pre, o);
+            if (lane >= o) pre += u;
+        }
+        const int total = __shfl_sync(kFull, pre, 31);
+        const int excl = pre - len;
+        for (int j0 = 0; j0 < total; j0 += 32) {
+            const int j = j0 + lane;
+            int pos = 0;  // number of segments that end at or before j = the segment holding j
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+                const int v = __shfl_sync(kFull, pre, pos + step - 1);
+                if (v <= j) pos += step;
+            }
+            const int p = __shfl_sync(kFull, lo, pos) + (j - __shfl_sync(kFull, excl, pos));
+            double d2 = CMX_INF;
+            if (j < total) {
+                // bit-identical to cKDTree: plain float64 dx*dx + dy*dy, no FMA contraction
+                const double da = __dsub_rn(ta, a.bin_a[p]);
+                const double db = __dsub_rn(tb, a.bin_b[p]);
+                d2 = __dadd_rn(__dmul_rn(da, da), __dmul_rn(db, db));
+                if (!(d2 == d2)) d2 = CMX_INF;  // NaN never ranks
+            }
+            // ties at the k-th distance are resolved by index inside the merge, so '<=' here
+            const bool c = d2 <= kth && d2 < CMX_INF;
+            if (__any_sync(kFull, c)) {
+                double cd = c ? d2 : CMX_INF;
+                int ci = c ? a.bin_idx[p] : INT_MAX;
+                warp_sort32(cd, ci, lane);
+                if (empty) {  // first candidates of this target: the sorted chunk is the list
+                    ld[0] = cd;
+                    li[0] = ci;
+                    empty = false;
+                } else {
+                    merge_sorted32<E>(ld, li, cd, ci, lane);
+                }
+                double sel = ld[0];
+#pragma unroll
+                for (int e = 1; e < E; ++e)
+                    if (((k - 1) >> 5) == e) sel = ld[e];
+                kth = fmin(kth, __shfl_sync(kFull, sel, (k - 1) & 31));
+            }
+        }
+    }
+}
+
+// P = 0: neighbour table and / or the single-slice IDW epilogue.  P = 2, 4: short time / level batches (up to P * 32
+// slices) with the fused batch epilogue - a warp takes FOUR consecutive targets so that every lane (= batch element)
+// ends up with a 32-byte (16-byte for float32) row segment to store.
+template <int E, int P>
 __global__ void __launch_bounds__(256) knn_binned_kernel(const __grid_constant__ KnnArgs a) {
     const int lane = threadIdx.x & 31;
-    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const SeedGrid s = *a.seed;
     const int* __restrict__ sat = a.sat;
     const int k = a.j.k;
-    for (long long m = warp0; m < a.M; m += nwarps) {
-        double ta, tb;
-        if (a.j.grid) {
-            const long long row = m / a.j.n_b;
-            ta = a.j.t_a[row];
-            tb = a.j.t_b[m - row * a.j.n_b];
-        } else {
-            ta = a.j.t_a[m];
-            tb = a.j.t_b[m];
-        }
-        double ld[E];
-        int li[E];
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            ld[e] = CMX_INF;
-            li[e] = INT_MAX;
-        }
-        int ra0 = 0, ra1 = -1, cb0 = 0, cb1 = -1;
-        double kth = CMX_INF;
-        bool empty = true;
-        if (s.valid) {
-            kth = seed_bound_d2_warp(s, sat, ta, tb, k, lane);
-            if (kth < CMX_INF) {
-                const double D = sqrt(kth) * (1.0 + 1e-12);
-                ra0 = seed_cell(ta - D, s.a0, s.inv_h, s.ga);
-                ra1 = seed_cell(ta + D, s.a0, s.inv_h, s.ga);
-                cb0 = seed_cell(tb - D, s.b0, s.inv_h, s.gb);
-                cb1 = seed_cell(tb + D, s.b0, s.inv_h, s.gb);
-            } else {  // fewer than k finite samples (or a non-finite target): look at everything
-                ra1 = s.ga - 1;
-                cb1 = s.gb - 1;
-            }
-        }
-        const int R = ra1 - ra0 + 1;
-        for (int rb = 0; rb < R; rb += 32) {
-            int lo = 0, len = 0;
-            if (rb + lane < R) {
-                const int* S0 = sat + (size_t)(ra0 + rb + lane) * SAT_LD;
-                const int left = S0[SAT_LD + cb0] - S0[cb0];
-                lo = S0[s.gb] + left;
-                len = (S0[SAT_LD + cb1 + 1] - S0[cb1 + 1]) - left;
-            }
-            int pre = len;  // inclusive prefix sum of the segment lengths
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int u = __shfl_up_sync(kFull, pre, o);
-                if (lane >= o) pre += u;
-            }
-            const int total = __shfl_sync(kFull, pre, 31);
-            const int excl = pre - len;
-            for (int j0 = 0; j0 < total; j0 += 32) {
-                const int j = j0 + lane;
-                int pos = 0;  // number of segments that end at or before j = the segment holding j
-#pragma unroll
-                for (int step = 16; step >= 1; step >>= 1) {
-                    const int v = __shfl_sync(kFull, pre, pos + step - 1);
-                    if (v <= j) pos += step;
-                }
-                const int p = __shfl_sync(kFull, lo, pos) + (j - __shfl_sync(kFull, excl, pos));
-                double d2 = CMX_INF;
-                if (j < total) {
-                    // bit-identical to cKDTree: plain float64 dx*dx + dy*dy, no FMA contraction
-                    const double da = __dsub_rn(ta, a.bin_a[p]);
-                    const double db = __dsub_rn(tb, a.bin_b[p]);
-                    d2 = __dadd_rn(__dmul_rn(da, da), __dmul_rn(db, db));
-                    if (!(d2 == d2)) d2 = CMX_INF;  // NaN never ranks
-                }
-                // ties at the k-th distance are resolved by index inside the merge, so '<=' here
-                const bool c = d2 <= kth && d2 < CMX_INF;
-                if (__any_sync(kFull, c)) {
-                    double cd = c ? d2 : CMX_INF;
-                    int ci = c ? a.bin_idx[p] : INT_MAX;
-                    warp_sort32(cd, ci, lane);
-                    if (empty) {  // first candidates of this target: the sorted chunk is the list
-                        ld[0] = cd;
-                        li[0] = ci;
-                        empty = false;
-                    } else {
-                        merge_sorted32<E>(ld, li, cd, ci, lane);
-                    }
-                    double sel = ld[0];
-#pragma unroll
-                    for (int e = 1; e < E; ++e)
-                        if (((k - 1) >> 5) == e) sel = ld[e];
-                    kth = fmin(kth, __shfl_sync(kFull, sel, (k - 1) & 31));
+    // Work is handed out in CHUNKS of consecutive targets per CTA (not strided over the grid): consecutive targets share
+    // most of their neighbours, cells and table entries, so what one iteration pulled into L1 is reused by the next
+    // (the batch epilogue's value-row gathers hit L1 instead of L2).
+    const int CHUNK = a.chunk;  // units (targets, or groups of four targets) per CTA and chunk; a multiple of 8
+    const int wib = threadIdx.x >> 5;
+    if constexpr (P == 0) {
+        for (long long base = (long long)blockIdx.x * CHUNK; base < a.M; base += (long long)gridDim.x * CHUNK) {
+            const long long end = base + CHUNK < a.M ? base + CHUNK : a.M;
+            for (long long m = base + wib; m < end; m += 8) {
+                double ld[E];
+                int li[E];
+                binned_search_target<E>(a, s, sat, k, lane, m, ld, li);
+                const double r = finish_target<E>(a, lane, m, ld, li);
+                if (a.j.idw_mode == 1 && lane == 0) {
+                    if (a.j.value_is_f32)
+                        static_cast<float*>(a.j.out)[m] = (float)r;
+                    else
+                        static_cast<double*>(a.j.out)[m] = r;
                 }
             }
         }
-        const double r = finish_target<E>(a, lane, m, ld, li);
-        if (a.j.idw_mode == 1 && lane == 0) {
-            if (a.j.value_is_f32)
-                static_cast<float*>(a.j.out)[m] = (float)r;
-            else
-                static_cast<double*>(a.j.out)[m] = r;
+    } else {
+        constexpr int G = 4;
+        __shared__ BatchNbr strips[8][32 * E];
+        __shared__ double stage[8][G][P * 32];  // the group's results: [target][batch element]
+        BatchNbr* strip = strips[wib];
+        double (*st)[P * 32] = stage[wib];
+        const bool tables = a.j.idx_out || a.j.dist_out || a.j.d2_out;
+        const long long groups = (a.M + G - 1) / G;
+        for (long long base = (long long)blockIdx.x * CHUNK; base < groups; base += (long long)gridDim.x * CHUNK)
+        for (long long g = base + wib; g < (base + CHUNK < groups ? base + CHUNK : groups); g += 8) {
+            const long long m0 = g * G;
+            const int count = (int)(a.M - m0 < G ? a.M - m0 : G);
+            // a run-time loop: ONE copy of the search + epilogue code (four inlined copies overflow the instruction
+            // cache: ncu showed 21 no_instruction stalls per issue)
+#pragma unroll 1
+            for (int q = 0; q < count; ++q) {
+                double ld[E];
+                int li[E];
+                binned_search_target<E>(a, s, sat, k, lane, m0 + q, ld, li);
+                if (tables) finish_target<E>(a, lane, m0 + q, ld, li);
+                double r[P];
+                finish_batch<E, P>(a, lane, ld, li, strip, r);
+#pragma unroll
+                for (int p = 0; p < P; ++p) st[q][p * 32 + lane] = r[p];
+            }
+            __syncwarp();
+            double rr[G][P];
+#pragma unroll
+            for (int q = 0; q < G; ++q)
+#pragma unroll
+                for (int p = 0; p < P; ++p) rr[q][p] = q < count ? st[q][p * 32 + lane] : 0.0;
+            store_batch<P, G>(a, lane, m0, count, rr);
+            __syncwarp();
         }
     }
 }
 
 template <int E>
-int launch_binned(const KnnArgs& args, bool scatter, cudaStream_t stream) {
+int launch_binned(const KnnArgs& args_, bool scatter, cudaStream_t stream) {
     const int sms = sm_count();
+    KnnArgs args = args_;
+    {   // chunks of 64 units when that still gives every CTA slot work, else the finest split (8 = one unit per warp)
+        const long long units = args.j.idw_mode == 2 ? (args.M + 3) / 4 : args.M;
+        args.chunk = units >= 64LL * sms * 8 ? 64 : (units >= 16LL * sms * 8 ? 16 : 8);
+    }
     timing_begin(CMX_KERNEL_KNN_BINNED, stream);
     if (scatter) {  // (small sample sets: already done by seed_small_kernel; the cursors were cleared by the pre-pass)
         const long long pre = (args.j.n + 255) / 256;
@@ -1066,9 +1258,18 @@ int launch_binned(const KnnArgs& args, bool scatter, cudaStream_t stream) {
                                                            args.bin_cursor, args.bin_a, args.bin_b, args.bin_idx);
         note_launch();
     }
-    const long long blocks = (args.M * 32 + 255) / 256;
     const long long cap = (long long)sms * 8;
-    knn_binned_kernel<E><<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, stream>>>(args);
+    if (args.j.idw_mode == 2) {
+        const long long blocks = ((args.M + 3) / 4 + args.chunk - 1) / args.chunk;  // one chunk per CTA and round
+        const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+        if (args.j.n_batch <= 64)
+            knn_binned_kernel<E, 2><<<grid, 256, 0, stream>>>(args);
+        else
+            knn_binned_kernel<E, 4><<<grid, 256, 0, stream>>>(args);
+    } else {
+        const long long blocks = (args.M + args.chunk - 1) / args.chunk;  // one chunk per CTA and round
+        knn_binned_kernel<E, 0><<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, stream>>>(args);
+    }
     timing_end(CMX_KERNEL_KNN_BINNED, stream);
     note_launch();
     return check_launch();
@@ -1206,6 +1407,8 @@ int run_knn(const KnnJob& job, cudaStream_t stream) {
     if (job.k > CMX_MAX_K) return CMX_ERR_K_TOO_LARGE;
     if ((long long)job.k > job.n) return CMX_ERR_K_GT_N;
     if (job.idw_mode == 1 && (!job.vals || !job.out || job.k_min < 1)) return CMX_ERR_BAD_ARG;
+    if (job.idw_mode == 2 && (!job.vals || job.k_min < 1 || job.n_batch < 2 || job.n_batch > 128 || job.peers.n < 1))
+        return CMX_ERR_BAD_ARG;
     const long long M = job.grid ? job.n_a * job.n_b : job.n_a;
     if (M == 0) return CMX_OK;
     if (job.n > 0x7fffffffLL) return CMX_ERR_TOO_MANY;
@@ -1266,6 +1469,7 @@ int run_knn(const KnnJob& job, cudaStream_t stream) {
         b += (size_t)job.n * sizeof(int);
         if (b > ws_end) binned = false;  // does not fit (N beyond ~5e7 with the base workspace): K1 returns the same table
     }
+    if (job.idw_mode == 2 && !binned) return CMX_ERR_UNSUPPORTED;  // the fused batch epilogue lives in K1c only
 
     // ---- seed grid pre-pass: bbox -> geometry -> histogram -> summed-area table (-> counting sort) ----
     const bool small = job.n <= SMALL_N;

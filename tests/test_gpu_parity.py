@@ -685,3 +685,48 @@ def test_ok_reconstructor_native_fit_equals_scipy_fit(model):
     np.testing.assert_allclose(c.variogram_model_parameters, a.variogram_model_parameters, rtol=1e-3, atol=1e-5)
     if model != "gaussian":  # (zero-nugget gaussian: condition ~1e10 turns the 1e-7 parameter difference into ~1e-3)
         assert np.max(np.abs(fc - fa)) <= 1e-4 * np.max(np.abs(fa))
+
+
+# ------------------------------------------------------------------------------------------
+# fused batch epilogue of the cell-binned search (short batches: no [M][k] table round trip)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("t,k,dtype", [(2, 5, torch.float64), (33, 32, torch.float64), (37, 32, torch.float32),
+                                       (64, 32, torch.float32), (65, 40, torch.float64), (100, 64, torch.float32),
+                                       (127, 100, torch.float64)])
+def test_fused_batch_epilogue_equals_the_table_path(t, k, dtype):
+    """T < 128 with the binned search: weights applied inside knn_binned_kernel (finish_batch) - must give the very
+    bits of the table path (search + K2), on grids whose size is not a multiple of the 4-target groups, on sparse
+    targets, with and without non-finite values, with the neighbour table requested alongside."""
+    la, lo, _, rng = _samples(3000, 1000 + t)
+    vals = rng.normal(size=(3000, t))
+    if dtype == torch.float32:
+        vals = vals.astype(np.float32).astype(np.float64)
+    for grid in (True, False):
+        if grid:
+            tg = K.Targets.make(np.linspace(-70, 70, 31), np.linspace(-170, 170, 53), True, DEV)  # 1643 targets
+            q = dense_points(np.linspace(-70, 70, 31), np.linspace(-170, 170, 53))
+        else:
+            tl, to = rng.uniform(-90, 90, 1001), rng.uniform(-180, 180, 1001)
+            tg = K.Targets.make(tl, to, False, DEV)
+            q = sparse_points(tl, to)
+        for bad in (False, True):
+            v = vals.copy()
+            if bad:
+                v[rng.choice(3000, 700, replace=False), rng.integers(0, t, 700)] = np.nan
+                v[rng.choice(3000, 50, replace=False), 0] = np.inf
+            fused = K.idw(la, lo, v, tg, k=k, k_min=3, layout="sample_major", dtype=dtype, search="binned")
+            table = K.idw(la, lo, v, tg, k=k, k_min=3, layout="sample_major", dtype=dtype, search="brute")
+            assert fused.shape == (t, tg.count) and fused.dtype == dtype
+            assert torch.equal(torch.isnan(fused), torch.isnan(table))
+            assert torch.equal(torch.nan_to_num(fused), torch.nan_to_num(table))
+            with np.errstate(invalid="ignore"):
+                ref = idw_oracle_batched(sparse_points(la, lo), v.T, q, k=k, k_min=3)
+            got = fused.cpu().numpy().astype(np.float64)
+            assert np.array_equal(np.isnan(got), np.isnan(ref))
+            ok = ~np.isnan(ref)  # (zero-mean random values: measure against the field's scale, not value by value)
+            assert np.max(np.abs(got[ok] - ref[ok])) <= (1e-12 if dtype == torch.float64 else IDW_RTOL) * np.max(np.abs(ref[ok]))
+    out, dist, idx = K.idw(la, lo, vals, tg, k=k, layout="sample_major", dtype=dtype, search="binned", return_neighbours=True)
+    d0, i0 = knn_ckdtree(sparse_points(la, lo), q, k)
+    np.testing.assert_array_equal(idx.cpu().numpy(), i0)
+    np.testing.assert_array_equal(dist.cpu().numpy(), d0)
+    assert torch.equal(out, K.idw(la, lo, vals, tg, k=k, layout="sample_major", dtype=dtype, search="binned"))

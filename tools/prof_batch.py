@@ -14,7 +14,7 @@ run(); torch.cuda.synchronize()
 K.kernel_timing(True)
 e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
 e0.record(); out = run(); e1.record(); torch.cuda.synchronize()
-knn_ms, _ = K.kernel_time(K.KERNEL_KNN)
+knn_ms = K.kernel_time(K.KERNEL_KNN)[0] + K.kernel_time(K.KERNEL_KNN_BINNED)[0]
 K.kernel_timing(True); run(); torch.cuda.synchronize(); b_ms, _ = K.kernel_time(K.KERNEL_IDW_BATCH); K.kernel_timing(False)
 M = nlat * nlon
-print(f"N={N} M={M} T={T} k={k}: total {e0.elapsed_time(e1):.2f} ms, knn {knn_ms:.2f} ms, batch {b_ms:.2f} ms ({M*T*8/b_ms/1e6:.1f} GB/s written)")
+print(f"N={N} M={M} T={T} k={k}: total {e0.elapsed_time(e1):.2f} ms, search(+fused epilogue) {knn_ms:.2f} ms, K2 {b_ms:.2f} ms")
