@@ -50,6 +50,9 @@ SIGNATURES = {
     "cmx_variogram_edges": (c_int, [_P, c_int, _P, _P]),
     "cmx_variogram_fit": (c_int, [c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "cmx_ok_workspace_bytes": (c_size_t, [c_int, c_i64]),
+    "cmx_ok_global_workspace_bytes": (c_size_t, [c_i64]),
+    "cmx_ok_global_f64": (c_int, [_P, _P, _P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_double), c_int, c_int, c_double, c_double, _P, ctypes.POINTER(ctypes.c_int32), _P, c_size_t, _P]),
+    "cmx_ok_global_f32": (c_int, [_P, _P, _P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_double), c_int, c_int, c_double, c_double, _P, ctypes.POINTER(ctypes.c_int32), _P, c_size_t, _P]),
     "cmx_ok_mw_f64": (c_int, [_P, _P, _P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, c_int, c_int, _P, c_int, c_double, c_double, _P, _P, _P, _P, c_size_t, _OPT, _P]),
     "cmx_ok_mw_f32": (c_int, [_P, _P, _P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, c_int, c_int, _P, c_int, c_double, c_double, _P, _P, _P, _P, c_size_t, _OPT, _P]),
     "cmx_timing_enable": (None, [c_int]),

@@ -25,6 +25,7 @@ __all__ = [
     "variogram_fit_device",
     "fit_variogram_native",
     "ok_moving_window",
+    "ok_global",
     "knn3",
     "ok_solve",
     "launch_count",
@@ -538,6 +539,41 @@ def ok_moving_window(s_x, s_y, z, t_x, t_y, grid: bool, *, k: int, variogram_mod
     if return_sigmasq:
         return out, sig, nsing
     return out, nsing
+
+
+def ok_global(s_x, s_y, z, t_x, t_y, grid: bool, *, variogram_model: str, params, geographic: bool = False,
+              exact_values: bool = True, pseudo_inv: bool = False, out_scale: float = 1.0, out_shift: float = 0.0,
+              dtype: torch.dtype = torch.float64):
+    """Global ordinary kriging (the mode climatrix ships): pykrige ``execute(style, x, y)`` without a moving window.
+
+    One solve of the (N+1) x (N+1) system serves every target (``csrc/global_kriging.cu``: blocked Cholesky of the
+    shifted positive-definite matrix; ``pseudo_inv`` or a numerically singular matrix -> one-sided Jacobi SVD, N <= 4095).
+    Coordinates in the kriging frame.  Returns ``(field (M,), status)`` with status 0 = Cholesky, 1 = SVD fallback,
+    2 = numerically singular and too large for the SVD path (field undefined).
+    """
+    lib = _lib.load()
+    dev = _require_cuda(s_x.device if isinstance(s_x, torch.Tensor) else None)
+    s_x, s_y, z = _as_f64(s_x, dev), _as_f64(s_y, dev), _as_f64(z, dev)
+    t_x, t_y = _as_f64(t_x, dev), _as_f64(t_y, dev)
+    n = s_x.numel()
+    m = t_x.numel() * t_y.numel() if grid else t_x.numel()
+    if not grid and t_x.numel() != t_y.numel():
+        raise ValueError("xpoints and ypoints must have same dimensions when treated as listing discrete points.")
+    if isinstance(params, torch.Tensor):
+        params = params.detach().cpu().tolist()
+    vals = [float(v) for v in (params.tolist() if hasattr(params, "tolist") else list(params))]
+    p = (ctypes.c_double * 3)(*(vals + [0.0] * (3 - len(vals))))
+    status = ctypes.c_int32(0)
+    with torch.cuda.device(dev):
+        out = torch.empty(m, dtype=dtype, device=dev)
+        ws = torch.empty(int(lib.cmx_ok_global_workspace_bytes(n)), dtype=torch.uint8, device=dev)  # O(N^2): not cached
+        fn = lib.cmx_ok_global_f64 if dtype == torch.float64 else lib.cmx_ok_global_f32
+        rc = fn(_ptr(s_x), _ptr(s_y), _ptr(z), n, _ptr(t_x), t_x.numel(), _ptr(t_y), t_y.numel(), int(grid),
+                _lib.METRIC_GEOGRAPHIC if geographic else _lib.METRIC_EUCLIDEAN, _lib.VARIOGRAM_MODELS[variogram_model], p,
+                int(exact_values), int(pseudo_inv), float(out_scale), float(out_shift), _ptr(out), ctypes.byref(status),
+                _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "cmx_ok_global")
+    return out, int(status.value)
 
 
 def knn3(s_xyz, t_xyz, k: int):

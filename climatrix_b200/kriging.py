@@ -15,8 +15,9 @@ error types.  The reference delegates to the third-party ``pykrige`` package
 
 New keyword (BASELINE.json north_star): ``n_closest_points`` / ``k`` selects pykrige's
 moving-window mode, which climatrix does not expose.  Without it the reference's shipped
-global kriging is computed (dense (N+1)x(N+1) factorisation through torch.linalg =
-cuSOLVER/cuBLAS library calls, SURVEY.md section 8f row 2 -- not a hand-written kernel).
+global kriging is computed by the hand-written kernels of ``csrc/global_kriging.cu`` (one
+blocked Cholesky solve of the shifted (N+1)x(N+1) system for all targets; ``pseudo_inv`` and
+numerically singular systems through a one-sided Jacobi SVD) -- SURVEY.md section 8f row 2.
 """
 
 from __future__ import annotations
@@ -356,64 +357,32 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
         self.variogram_model_parameters = params
         return params
 
-    def _gamma_t(self, torch, params, d):
-        model = self.variogram_model
-        p = [float(v) for v in params]
-        if model == "linear":
-            return p[0] * d + p[1]
-        if model == "power":
-            return p[0] * d ** p[1] + p[2]
-        if model == "gaussian":
-            return p[0] * (1.0 - torch.exp(-(d**2.0) / (p[1] * 4.0 / 7.0) ** 2.0)) + p[2]
-        if model == "exponential":
-            return p[0] * (1.0 - torch.exp(-d / (p[1] / 3.0))) + p[2]
-        inner = p[0] * ((3.0 * d) / (2.0 * p[1]) - (d**3.0) / (2.0 * p[1] ** 3.0)) + p[2]
-        return torch.where(d <= p[1], inner, torch.full_like(d, p[0] + p[2]))
-
-    def _dist_t(self, torch, ax, ay, bx, by, geographic):
-        if not geographic:
-            return torch.cdist(torch.stack((ax, ay), 1), torch.stack((bx, by), 1), compute_mode="donot_use_mm_for_euclid_dist")
-        rad = np.pi / 180.0
-        lat1, lat2 = ay[:, None] * rad, by[None, :] * rad
-        dlon = (ax[:, None] - bx[None, :]) * rad
-        c1, s1, c2, s2, cd = torch.cos(lat1), torch.sin(lat1), torch.cos(lat2), torch.sin(lat2), torch.cos(dlon)
-        return 180.0 / np.pi * torch.atan2(
-            torch.sqrt((c2 * torch.sin(dlon)) ** 2 + (c1 * s2 - s1 * c2 * cd) ** 2), s1 * s2 + c1 * c2 * cd
-        )
-
     def _global(self, torch, dev, xs, ys, zs, xpts, ypts, sparse_target, xc, yc, scaling, params, geographic,
                 v_mean, v_std, tdtype):
-        """The reference's shipped mode: one (N+1)x(N+1) system for all targets (pykrige _exec_vector /
-        _exec_loop).  LIBRARY path (torch.linalg -> cuSOLVER, torch.matmul -> cuBLAS), float64."""
-        n = xs.numel()
-        a = torch.zeros((n + 1, n + 1), dtype=torch.float64, device=dev)
-        a[:n, :n] = -self._gamma_t(torch, params, self._dist_t(torch, xs, ys, xs, ys, geographic))
-        a.fill_diagonal_(0.0)
-        a[n, :] = 1.0
-        a[:, n] = 1.0
-        a[n, n] = 0.0
-        a_inv = torch.linalg.pinv(a) if self.pseudo_inv else torch.linalg.inv(a)
-        if sparse_target:
-            gx, gy = xpts, ypts
-        else:
-            gxm, gym = np.meshgrid(xpts, ypts)
-            gx, gy = gxm.ravel(), gym.ravel()
-        if not geographic:
-            gx, gy = _anisotropy(gx, gy, xc, yc, scaling)
-        gx_t = torch.as_tensor(np.ascontiguousarray(gx)).to(dev)
-        gy_t = torch.as_tensor(np.ascontiguousarray(gy)).to(dev)
-        m = gx_t.numel()
-        out = torch.empty(m, dtype=torch.float64, device=dev)
-        chunk = max(1, min(m, (1 << 27) // max(1, n + 1)))
-        for s in range(0, m, chunk):
-            e = min(m, s + chunk)
-            bd = self._dist_t(torch, gx_t[s:e], gy_t[s:e], xs, ys, geographic)
-            b = torch.ones((e - s, n + 1), dtype=torch.float64, device=dev)
-            g = -self._gamma_t(torch, params, bd)
-            b[:, :n] = torch.where(bd.abs() <= EPS, torch.zeros_like(g), g)
-            x = b @ a_inv.T
-            out[s:e] = x[:, :n] @ zs
-        return (out * v_std + v_mean).to(tdtype).cpu().numpy()
+        """The reference's shipped mode: one (N+1) x (N+1) system for all targets (pykrige _exec_vector / _exec_loop),
+        on the hand-written kernels of ``csrc/global_kriging.cu`` (``cmx_ok_global_*``)."""
+        from . import kernels
+
+        if geographic:
+            tx, ty = xpts, ypts
+        elif sparse_target:
+            tx, ty = _anisotropy(xpts, ypts, xc, yc, scaling)
+        else:  # for a grid, anisotropy (angle 0) acts on the axes separately
+            tx, _ = _anisotropy(xpts, np.full_like(xpts, yc), xc, yc, scaling)
+            _, ty = _anisotropy(np.full_like(ypts, xc), ypts, xc, yc, scaling)
+        try:
+            out, status = kernels.ok_global(xs, ys, zs, tx, ty, not sparse_target, variogram_model=self.variogram_model,
+                                            params=params, geographic=geographic, exact_values=True,
+                                            pseudo_inv=bool(self.pseudo_inv), out_scale=float(v_std), out_shift=float(v_mean),
+                                            dtype=tdtype)
+        except NotImplementedError as exc:
+            raise NotImplementedError(
+                "pseudo_inv=True is available for at most 4095 samples (one-sided Jacobi SVD of the bordered matrix); "
+                "use the moving window (n_closest_points=k) for larger sample sets") from exc
+        if status == 2:
+            # scipy.linalg.inv raises LinAlgError("singular matrix") for the reference in the exactly singular case
+            raise np.linalg.LinAlgError("the global kriging matrix is numerically singular")
+        return out.cpu().numpy()
 
     @property
     def num_params(self) -> int:

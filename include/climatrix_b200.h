@@ -20,6 +20,8 @@
  *   cmx_ok_mw_f64/_f32 <- pykrige OrdinaryKriging.execute(backend="loop",
  *                         n_closest_points=k), call site kriging.py:236-241
  *   cmx_knn3, cmx_ok_solve_* <- the same call with coordinates_type="geographic"
+ *   cmx_ok_global_*    <- the same call WITHOUT n_closest_points (global kriging, what climatrix ships)
+ *   cmx_variogram_fit* <- pykrige core._calculate_variogram_model (scipy least_squares, soft_l1)
  *
  * Conventions
  *  - All data pointers are DEVICE pointers owned by the caller; nothing is
@@ -289,6 +291,31 @@ int cmx_ok_solve_f32(const double* s_x, const double* s_y, const double* z, int6
                      double out_scale, double out_shift,
                      float* out, float* sigmasq_out, int32_t* n_singular,
                      void* workspace, size_t workspace_bytes, const cmx_options* options, void* stream);
+
+/* ---- ordinary kriging, global (the mode climatrix ships: method="ok" without a neighbour count) ----
+ *
+ * pykrige OrdinaryKriging.execute(style, x, y, backend="vectorized"|"loop") without n_closest_points, reached from
+ * kriging.py:236-241: one (N+1) x (N+1) system for all targets.  climatrix keeps only the estimate, and
+ * z_t = b_t' A^-1 [Z; 0], so ONE solve A [w; lambda] = [Z; 0] serves every target (z_t = sum_i w_i b_ti + lambda):
+ * blocked Cholesky of the equivalent positive-definite matrix A + c0 11' (hand-written FP64 kernels);
+ * pseudo_inv != 0 (scipy.linalg.pinv semantics: singular values <= (N+1) eps s_max dropped) or a numerically singular
+ * matrix -> one-sided Jacobi SVD of the bordered matrix, available for N + 1 <= 4096 (CMX_ERR_UNSUPPORTED beyond
+ * when pseudo_inv is requested).
+ * Coordinates in the kriging frame like cmx_ok_mw_*; metric CMX_METRIC_GEOGRAPHIC uses great-circle distances.
+ * *status (HOST int, may be NULL; the call synchronises the stream once to read the factorisation flag):
+ *   0 Cholesky path, 1 fell back to the SVD path, 2 numerically singular and too large for the SVD path (out untouched).
+ */
+size_t cmx_ok_global_workspace_bytes(int64_t n_samples);
+int cmx_ok_global_f64(const double* s_x, const double* s_y, const double* z, int64_t n_samples,
+                      const double* t_x, int64_t n_x, const double* t_y, int64_t n_y, int target_is_grid,
+                      int metric, int variogram_model, const double params[3], int exact_values, int pseudo_inv,
+                      double out_scale, double out_shift, double* out, int32_t* status,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int cmx_ok_global_f32(const double* s_x, const double* s_y, const double* z, int64_t n_samples,
+                      const double* t_x, int64_t n_x, const double* t_y, int64_t n_y, int target_is_grid,
+                      int metric, int variogram_model, const double params[3], int exact_values, int pseudo_inv,
+                      double out_scale, double out_shift, float* out, int32_t* status,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* total scratch for cmx_ok_mw_* (includes the kNN scratch and cmx_ok_solve_workspace_bytes) */
 size_t cmx_ok_workspace_bytes(int k, int64_t n_targets);

@@ -427,9 +427,10 @@ def test_ok_reconstructor_moving_window_matches_golden(name, dtype):
     assert np.max(np.abs(got - g["expected"])) <= OK_RTOL * scale
 
 
-@pytest.mark.parametrize("name", [n for n in golden_names("ok_global_") if "gaussian" not in n and "pinv" not in n])
+@pytest.mark.parametrize("name", golden_names("ok_global_"))
 def test_ok_reconstructor_global_mode_matches_golden(name):
-    """The reference's shipped global kriging (library path, torch.linalg)."""
+    """The reference's shipped global kriging on the hand-written kernels (csrc/global_kriging.cu): blocked Cholesky of
+    the shifted system; ``pseudo_inv`` (ok_global_points_pinv) through the one-sided Jacobi SVD."""
     g = load_golden(name)
     src = sparse_dataset(g["sample_lat"], g["sample_lon"], np.asarray(g["values"]).reshape(-1, 1))
     tgt = cm.Domain.from_lat_lon(g["target_lat"], g["target_lon"], kind="sparse" if g["meta"]["target_sparse"] else "dense")
@@ -437,8 +438,91 @@ def test_ok_reconstructor_global_mode_matches_golden(name):
         warnings.simplefilter("ignore")
         out = cm.OrdinaryKrigingReconstructor(src, tgt, **g["meta"]["kwargs"]).reconstruct()
     got = np.asarray(out.da.values, dtype=np.float64)
+    assert got.shape == g["expected"].shape
     scale = np.max(np.abs(g["expected"]))
+    if name == "ok_global_gaussian":
+        # Gaussian model, zero nugget, 300 samples: cond(A) = 9e15.  The fixture is LAPACK's rounding noise - two LAPACK
+        # routes (inv vs solve) already differ by 1.5e-2 on it - so no implementation can reproduce it; ours detects the
+        # numerically singular system and takes the SVD path.  Checked: finite, and of the field's magnitude.
+        assert np.isfinite(got).all() and np.max(np.abs(got)) <= 10.0 * scale
+        return
     assert np.max(np.abs(got - g["expected"])) <= OK_RTOL * scale
+
+
+def _dense_global_reference(x, y, z, tx, ty, model, params, geographic=False, pinv=False):
+    """NumPy / SciPy statement of pykrige's global solve: [[-gamma(D), 1], [1', 0]] x = [-gamma(d); 1], z = x . Z."""
+    import scipy.linalg
+    from scipy.spatial.distance import cdist
+
+    n = len(x)
+    f = pk.VARIOGRAM_FUNCTIONS[model]
+    if geographic:
+        d = pk.great_circle_distance(x[:, None], y[:, None], x, y)
+        bd = pk.great_circle_distance(tx[:, None], ty[:, None], x, y)
+    else:
+        d = cdist(np.stack((x, y), 1), np.stack((x, y), 1))
+        bd = cdist(np.stack((tx, ty), 1), np.stack((x, y), 1))
+    a = np.zeros((n + 1, n + 1))
+    a[:n, :n] = -f(params, d)
+    np.fill_diagonal(a, 0.0)
+    a[n, :n] = a[:n, n] = 1.0
+    b = np.ones((len(tx), n + 1))
+    g = -f(params, bd)
+    b[:, :n] = np.where(np.abs(bd) <= 1e-10, 0.0, g)
+    a_inv = scipy.linalg.pinv(a) if pinv else scipy.linalg.inv(a)
+    return (b @ a_inv.T)[:, :n] @ z
+
+
+@pytest.mark.parametrize("model,params,n,geo", [
+    ("spherical", [1.1, 0.6, 0.05], 1037, False), ("linear", [0.8, 0.02], 700, False), ("power", [0.7, 1.4, 0.03], 64, False),
+    ("exponential", [0.9, 0.7, 0.01], 1500, False), ("gaussian", [1.0, 0.3, 0.05], 333, False), ("spherical", [1.0, 40.0, 0.02], 500, True),
+    ("spherical", [1.0, 0.5, 0.0], 1, False), ("linear", [1.0, 0.0], 2, False),
+])
+def test_global_kriging_kernels_match_a_dense_numpy_solve(model, params, n, geo):
+    """cmx_ok_global: several 64-blocks with a ragged last one, every model, grid and point targets, float32 output."""
+    rng = np.random.default_rng(n)
+    if geo:
+        x, y = rng.uniform(0, 360, n), rng.uniform(-80, 80, n)
+        tx, ty = rng.uniform(0, 360, 900), rng.uniform(-80, 80, 900)
+    else:
+        x, y = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+        tx, ty = rng.uniform(-1.1, 1.1, 900), rng.uniform(-1.1, 1.1, 900)
+    tx[:min(n, 20)], ty[:min(n, 20)] = x[:min(n, 20)], y[:min(n, 20)]  # exact hits
+    z = np.sin(3 * x) + np.cos(2 * y) + 0.2 * rng.normal(size=n)
+    out, status = K.ok_global(x, y, z, tx, ty, False, variogram_model=model, params=params, geographic=geo,
+                              out_scale=2.0, out_shift=0.5)
+    ref = _dense_global_reference(x, y, z, tx, ty, model, params, geo) * 2.0 + 0.5
+    assert status in (0, 1)
+    assert np.max(np.abs(out.cpu().numpy() - ref)) <= 1e-8 * max(np.max(np.abs(ref)), 1.0)
+    if not geo and n > 10:
+        gx, gy = np.linspace(-1, 1, 37), np.linspace(-1, 1, 23)
+        out, status = K.ok_global(x, y, z, gx, gy, True, variogram_model=model, params=params, dtype=torch.float32)
+        mx, my = np.meshgrid(gx, gy)
+        ref = _dense_global_reference(x, y, z, mx.ravel(), my.ravel(), model, params)
+        assert out.dtype == torch.float32 and out.numel() == 37 * 23
+        assert np.max(np.abs(out.double().cpu().numpy() - ref)) <= 1e-6 * max(np.max(np.abs(ref)), 1.0)
+
+
+def test_global_kriging_pseudo_inverse_on_a_singular_system():
+    """Duplicate samples with a zero nugget make A exactly singular: scipy.linalg.inv fails, pykrige's pseudo_inv=True
+    uses scipy.linalg.pinv.  Ours: one-sided Jacobi SVD with the same cut-off; without pseudo_inv the Cholesky detects
+    the singular system and falls back to the same path (status 1)."""
+    rng = np.random.default_rng(5)
+    n = 240
+    x, y = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    x[10:20], y[10:20] = x[:10], y[:10]
+    z = np.sin(3 * x) + 0.1 * rng.normal(size=n)
+    z[10:20] = z[:10]
+    tx, ty = rng.uniform(-1, 1, 400), rng.uniform(-1, 1, 400)
+    params = [1.0, 0.6, 0.0]
+    ref = _dense_global_reference(x, y, z, tx, ty, "spherical", params, pinv=True)
+    for pinv in (True, False):
+        out, status = K.ok_global(x, y, z, tx, ty, False, variogram_model="spherical", params=params, pseudo_inv=pinv)
+        assert status == (0 if pinv else 1) or pinv
+        assert np.max(np.abs(out.cpu().numpy() - ref)) <= 1e-7 * np.max(np.abs(ref))
+    with pytest.raises(NotImplementedError):
+        K.ok_global(np.zeros(5000), np.arange(5000.0), np.zeros(5000), tx, ty, False, variogram_model="linear", params=[1, 0],
+                    pseudo_inv=True)
 
 
 def test_ok_config2_full_size_sample_vs_oracle():
