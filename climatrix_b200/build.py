@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.environ.get("CMX_LIB") or os.path.join(LIB_DIR, "libclimatrix_b200.so")  # CMX_LIB: tuning variants
 SOURCES = ["capi.cu", "knn.cu", "knn3.cu", "idw.cu", "variogram.cu", "kriging.cu", "global_kriging.cu"]
-HEADERS = ["common.cuh", "rerank.cuh", "ok_chol.cuh", "variogram_fit.cuh", os.path.join("..", "..", "include", "climatrix_b200.h")]
+HEADERS = ["common.cuh", "rerank.cuh", "ok_chol.cuh", "ok_chol2.cuh", "variogram_fit.cuh", os.path.join("..", "..", "include", "climatrix_b200.h")]
 
 # variogram.cu holds the restated SciPy TRF fit: its stopping tests compare finite-difference noise with 1e-8, so the
 # device build must round like the host build (no multiply-add contraction) to stop at the same iterate

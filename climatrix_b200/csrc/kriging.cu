@@ -765,6 +765,10 @@ __global__ void __launch_bounds__(TEAMS * ((KC + 31) / 32) * 32, KC > 32 ? 3 : 4
 }  // namespace cmx
 
 #include "ok_chol.cuh"
+#include "ok_chol2.cuh"
+#ifndef CMX_CHOL_PAIRS
+#define CMX_CHOL_PAIRS 1  // 1: two columns per step (ok_chol2.cuh); 0: one column per step (ok_chol.cuh)
+#endif
 
 namespace cmx {
 namespace {
@@ -876,10 +880,16 @@ int solve_table(const double* s_x, const double* s_y, const double* z, long long
         int* fail_count = reinterpret_cast<int*>(sc);
         int* fail_list = reinterpret_cast<int*>(sc + 256);
         CMX_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(int), stream));
+        // k <= 48: one column per step; above: two (measured: 13.8 vs 15.1 ms at k = 48, 29.1 vs 28.6 ms at k = 64 per
+        // 1.04 M windows with the same assembly; the pair kernel then gained the per-model register assembly)
         if (k <= 16) rc = launch_ok_chol<2>(a, fail_list, fail_count, stream);
         else if (k <= 32) rc = launch_ok_chol<4>(a, fail_list, fail_count, stream);
         else if (k <= 48) rc = launch_ok_chol<6>(a, fail_list, fail_count, stream);
+#if CMX_CHOL_PAIRS
+        else rc = launch_ok_chol2<8>(a, fail_list, fail_count, stream);
+#else
         else rc = launch_ok_chol<8>(a, fail_list, fail_count, stream);
+#endif
         if (rc == CMX_OK) {
             a.list = fail_list;
             a.list_count = fail_count;

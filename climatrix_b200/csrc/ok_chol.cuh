@@ -89,35 +89,61 @@ __device__ __forceinline__ double rsqrt_pos(double d) {
     return y;
 }
 
+// gamma of a Euclidean pair from its SQUARED distance: no square root for the Gaussian model, the spherical
+// polynomial folded to two multiply-adds; d2 = 0 gives exactly gamma(0) (the clamp only feeds the reciprocal root)
+template <int MODEL>
+__device__ __forceinline__ double gamma_from_d2(const VarioConst& v, double d2, double sA, double sB, double r2) {
+    if (MODEL == CMX_VARIOGRAM_GAUSSIAN) return v.p0 * (1.0 - exp(-d2 * v.c0)) + v.p2;
+    const double d = d2 * rsqrt_pos(fmax(d2, 1.0e-290));
+    if (MODEL == CMX_VARIOGRAM_SPHERICAL) return d2 <= r2 ? fma(d, fma(-sB, d2, sA), v.p2) : v.p0 + v.p2;
+    return gamma_model<MODEL>(v, d);
+}
+
 // gamma of every sample pair (i, m), m < i < k, into tri[i (i - 1) / 2 + m]; returns this lane's largest value.
 // Rows p and k - p are folded into one sweep of k elements, so every 32-lane pass is full (k = 64: 64 passes for
-// 2016 pairs) and the index arithmetic is two selects; two passes are in flight per lane (independent chains).
-template <int MODEL, int METRIC>
+// 2016 pairs) and the index arithmetic is a few selects.  Used for the geographic metric and for k > 48; smaller
+// Euclidean windows are assembled straight into registers (chol_assemble_direct).
+template <int MODEL, int METRIC, int PASSES = 2>
 __device__ __forceinline__ double chol_pair_gammas(const VarioConst& vc, const double2* __restrict__ xy, double* __restrict__ tri,
                                                    int k, int lane) {
-    double gmax = 0.0;
-    for (int p = 1; 2 * p <= k; ++p) {
-        const int ia = p, ib = k - p;                  // row ia: columns 0 .. p-1; row ib: columns 0 .. k-p-1
-        const int count = ia == ib ? p : k;            // k even: the middle row stands alone
-        const int offa = ia * (ia - 1) / 2, offb = ib * (ib - 1) / 2 - p;
-#pragma unroll 2
-        for (int e = lane; e < count; e += 32) {
-            const bool first = e < p;
-            const double2 pi = xy[first ? ia : ib];
-            const double2 pm = xy[first ? e : e - p];
-            double d;
-            if (METRIC == CMX_METRIC_EUCLIDEAN) {
-                const double dx = pi.x - pm.x, dy = pi.y - pm.y;
-                const double d2 = fma(dy, dy, dx * dx);
-                d = d2 > 1.0e-290 ? d2 * rsqrt_pos(d2) : 0.0;
-            } else {
-                d = sample_distance(METRIC, pi.x, pi.y, pm.x, pm.y);
+    constexpr int U = METRIC == CMX_METRIC_EUCLIDEAN ? 8 / PASSES : 2;
+    double gm[U][PASSES];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int q = 0; q < PASSES; ++q) gm[u][q] = 0.0;
+    const double sA = vc.p0 * vc.c0, sB = vc.p0 * vc.c1, r2 = vc.p1 * vc.p1;
+    const int half = k >> 1;
+    for (int p0 = 1; p0 <= half; p0 += U) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = p0 + u;
+            const int ia = p, ib = k - p;                         // row ia: columns 0 .. p-1; row ib: columns 0 .. k-p-1
+            const int count = p > half ? 0 : (ia == ib ? p : k);  // k even: the middle row stands alone
+            const int offa = ia * (ia - 1) / 2, offb = ib * (ib - 1) / 2 - p;
+#pragma unroll
+            for (int q = 0; q < PASSES; ++q) {
+                const int e = lane + 32 * q;
+                const bool live = e < count, first = e < p;
+                const double2 pi = xy[live ? (first ? ia : ib) : 0];
+                const double2 pm = xy[live ? (first ? e : e - p) : 0];
+                double g;
+                if (METRIC == CMX_METRIC_EUCLIDEAN) {
+                    const double dx = pi.x - pm.x, dy = pi.y - pm.y;
+                    g = gamma_from_d2<MODEL>(vc, fma(dy, dy, dx * dx), sA, sB, r2);
+                } else {
+                    g = gamma_model<MODEL>(vc, sample_distance(METRIC, pi.x, pi.y, pm.x, pm.y));
+                }
+                if (live) tri[(first ? offa : offb) + e] = g;
+                gm[u][q] = fmax(gm[u][q], g);  // idle slots evaluate gamma(0), never above a real pair's value
             }
-            const double g = gamma_model<MODEL>(vc, d);
-            tri[(first ? offa : offb) + e] = g;
-            gmax = fmax(gmax, g);
         }
     }
+    double gmax = 0.0;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int q = 0; q < PASSES; ++q) gmax = fmax(gmax, gm[u][q]);
     return gmax;
 }
 
@@ -130,6 +156,7 @@ template <int NB, int MODEL>
 __device__ __forceinline__ double chol_assemble_direct(const VarioConst& vc, const double2* __restrict__ xy, int k, int r,
                                                        int c, double (&t)[NB + 1][2 * NB]) {
     double gmax = 0.0;
+    const double sA = vc.p0 * vc.c0, sB = vc.p0 * vc.c1, r2 = vc.p1 * vc.p1;
 #pragma unroll
     for (int a = 0; a < NB; ++a) {
         if (a % 2 == 0) chol_phase_sync();
@@ -141,9 +168,7 @@ __device__ __forceinline__ double chol_assemble_direct(const VarioConst& vc, con
                 const int mm = 4 * b + c;
                 const double2 pm = xy[mm];
                 const double dx = pi.x - pm.x, dy = pi.y - pm.y;
-                const double d2 = fma(dy, dy, dx * dx);
-                const double d = d2 > 1.0e-290 ? d2 * rsqrt_pos(d2) : 0.0;
-                double g = gamma_model<MODEL>(vc, d);
+                double g = gamma_from_d2<MODEL>(vc, fma(dy, dy, dx * dx), sA, sB, r2);
                 g = (mm < i && i < k) ? g : 0.0;
                 t[a][b] = g;
                 gmax = fmax(gmax, g);
