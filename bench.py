@@ -562,6 +562,15 @@ class Runner:
                       if name in ("c3", "c4", "c5") else "working set fits the 126 MB L2 (latency-bound configuration); no explicit flush"}
 
     # ---- ordinary-kriging workloads ----
+    @staticmethod
+    def _k4_traffic(k, windows):
+        """DRAM bytes of one K4 launch from the committed ncu capture (per window, scaled to this launch), or None."""
+        try:
+            per_window = json.load(open(os.path.join(ROOT, "profiles", "knn_traffic.json")))["k4_bytes_per_window"].get(str(k))
+        except Exception:  # noqa: BLE001
+            return None
+        return per_window * windows if per_window else None
+
     def run_ok(self, name, steps, warmup, search, with_e2e, with_cpu):
         torch, K, dev, world, rank = self.torch, self.K, self.dev, self.world, self.rank
         from climatrix_b200.kriging import _minmax_scale
@@ -604,13 +613,15 @@ class Runner:
         peak_nominal = self.sms * 64 * 2 * (run["clocks"]["sm_max_mhz"] or 1965.0) * 1e6 / 1e12
         peak_measured = K.fp64_peak_tflops()
         roofline = {
-            "kernel": "ok_chol_kernel (K4: register Cholesky of the shifted kriging system) + pivoted kernel on its hand-over list",
+            "kernel": ("ok_chol2_kernel (K4: register Cholesky of the shifted kriging system, two columns per step)" if k > 48 else
+                       "ok_chol_kernel (K4: register Cholesky of the shifted kriging system)") + " + pivoted kernel on its hand-over list",
             "bound": "fp64", "achieved": achieved, "peak": peak_measured, "unit": "TFLOP/s",
             "frac": (achieved / peak_measured) if achieved and peak_measured > 0 else None,
             "peak_source": "DFMA chains measured live in this run (cmx_fp64_peak_tflops)",
             "peak_nominal": peak_nominal, "frac_of_nominal": (achieved / peak_nominal) if achieved else None,
             "algorithmic_flops_per_window": flop_window, "algorithmic_flops_per_launch": flops,
-            "kernel_ms_avg": k4_avg, "launches_timed": k4_n, "share_of_step": k4_avg / ms if ms else None, "traffic": None,
+            "kernel_ms_avg": k4_avg, "launches_timed": k4_n, "share_of_step": k4_avg / ms if ms else None,
+            "traffic": self._k4_traffic(k, rows_local * n_lon),
         }
         other = {}
         for key, label in (("knn", "knn_kernel"), ("knn_binned", "knn_binned_kernel")):
