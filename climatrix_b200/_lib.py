@@ -43,6 +43,11 @@ SIGNATURES = {
     "cmx_idw_f32": (c_int, [_P, _P, c_i64, _P, c_i64, c_int, _P, c_i64, _P, c_i64, c_int, c_int, c_int, c_double, _P, _P, _P, _P, c_size_t, _OPT, _P]),
     "cmx_idw_apply_f64": (c_int, [_P, _P, c_i64, c_int, _P, c_i64, c_i64, c_int, c_int, c_int, c_double, _P, _P, _OPT, _P]),
     "cmx_idw_apply_f32": (c_int, [_P, _P, c_i64, c_int, _P, c_i64, c_i64, c_int, c_int, c_int, c_double, _P, _P, _OPT, _P]),
+    "cmx_score_workspace_bytes": (c_size_t, [c_i64]),
+    "cmx_idw_score_f64": (c_int, [_P, _P, c_i64, c_int, _P, c_i64, c_int, c_int, c_double, _P, _P, _P, _P, c_size_t, _P]),
+    "cmx_idw_score_f32": (c_int, [_P, _P, c_i64, c_int, _P, c_i64, c_int, c_int, c_double, _P, _P, _P, _P, c_size_t, _P]),
+    "cmx_score_f64": (c_int, [_P, _P, c_i64, _P, _P, c_size_t, _P]),
+    "cmx_score_f32": (c_int, [_P, _P, c_i64, _P, _P, c_size_t, _P]),
     "cmx_variogram_minmax": (c_int, [_P, _P, c_i64, c_int, c_int, c_int, _P, _P]),
     "cmx_variogram_workspace_bytes": (c_size_t, [c_int]),
     "cmx_variogram_bins": (c_int, [_P, _P, _P, c_i64, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),

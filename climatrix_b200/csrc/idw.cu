@@ -421,15 +421,71 @@ __global__ void __launch_bounds__(UTHREADS, 5) idw_batch_union_kernel(
     }
 }
 
-// single slice from a table: one warp per target (HPO inner loop, small problems)
+// Score of a field against held-out values, NaN-aware like the reference's nanmean (comparison.py:268-306): a target
+// counts when prediction and truth are both finite.  Deterministic: per-CTA partials in fixed slots, one CTA adds them
+// in a fixed order.  part: [n_ctas][3] = sum |d|, sum d^2, count.
+constexpr int SCORE_CTAS = 1024;  // grid of the stand-alone score kernel
+__device__ __forceinline__ void score_cta_partial(double ad, double sq, double cnt, double* __restrict__ part) {
+    __shared__ double s_part[3][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    ad = warp_sum(ad);
+    sq = warp_sum(sq);
+    cnt = warp_sum(cnt);
+    if (lane == 0) {
+        s_part[0][warp] = ad;
+        s_part[1][warp] = sq;
+        s_part[2][warp] = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_part[threadIdx.x][w];
+        part[(size_t)blockIdx.x * 3 + threadIdx.x] = t;
+    }
+}
+__global__ void score_reduce_kernel(const double* __restrict__ part, long long n_ctas, double* __restrict__ sums) {
+    __shared__ double s[3][256];
+    double a[3] = {0.0, 0.0, 0.0};
+    for (long long i = threadIdx.x; i < n_ctas; i += 256)
+        for (int q = 0; q < 3; ++q) a[q] += part[i * 3 + q];
+    for (int q = 0; q < 3; ++q) s[q][threadIdx.x] = a[q];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o)
+            for (int q = 0; q < 3; ++q) s[q][threadIdx.x] += s[q][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) sums[threadIdx.x] = s[threadIdx.x][0];
+}
 template <typename V>
-__global__ void idw_apply_single_kernel(const int* __restrict__ idx, const double* __restrict__ dd,
-                                        int dist_is_squared, long long M, int k_table, int k_use, int k_min,
-                                        double power, const V* __restrict__ vals, long long n_samples,
-                                        long long stride_i, V* __restrict__ out) {
+__global__ void __launch_bounds__(256) score_kernel(const V* __restrict__ pred, const V* __restrict__ truth, long long n,
+                                                     double* __restrict__ part) {
+    double ad = 0.0, sq = 0.0, cnt = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double d = (double)pred[i] - (double)truth[i];
+        if (isfinite(d)) {
+            ad += fabs(d);
+            sq = fma(d, d, sq);
+            cnt += 1.0;
+        }
+    }
+    score_cta_partial(ad, sq, cnt, part);
+}
+
+// single slice from a table: one warp per target (HPO inner loop, small problems).  SCORE: the trial's error against
+// held-out values is reduced in the same kernel (`out` may then be null: the field is never written).
+template <typename V, bool SCORE>
+__global__ void __launch_bounds__(256) idw_apply_single_kernel(const int* __restrict__ idx, const double* __restrict__ dd,
+                                                                int dist_is_squared, long long M, int k_table, int k_use,
+                                                                int k_min, double power, const V* __restrict__ vals,
+                                                                long long n_samples, long long stride_i, V* __restrict__ out,
+                                                                const V* __restrict__ truth, double* __restrict__ part) {
     const int lane = threadIdx.x & 31;
     const long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (m >= M) return;
+    if (m >= M) {
+        if (SCORE) score_cta_partial(0.0, 0.0, 0.0, part);
+        return;
+    }
     double w[CMX_MAX_K / 32];
     double wsum = 0.0;
 #pragma unroll
@@ -463,7 +519,20 @@ __global__ void idw_apply_single_kernel(const int* __restrict__ idx, const doubl
     den = warp_sum(den);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) fin += __shfl_xor_sync(kFull, fin, o);
-    if (lane == 0) out[m] = (fin < k_min || den == 0.0) ? quiet_nan<V>() : (V)(num / den);
+    const V r = (fin < k_min || den == 0.0) ? quiet_nan<V>() : (V)(num / den);
+    if (lane == 0 && out) out[m] = r;
+    if (SCORE) {
+        double ad = 0.0, sq = 0.0, cnt = 0.0;
+        if (lane == 0) {
+            const double d = (double)r - (double)truth[m];  // the field as stored (rounded to V), like the reference
+            if (isfinite(d)) {
+                ad = fabs(d);
+                sq = d * d;
+                cnt = 1.0;
+            }
+        }
+        score_cta_partial(ad, sq, cnt, part);
+    }
 }
 
 template <typename V>
@@ -492,9 +561,8 @@ int idw_from_table(const int* idx, const double* dd, int dist_is_squared, long l
     if (n_batch == 1) {
         const int threads = 256;
         const long long blocks = (M * 32 + threads - 1) / threads;
-        idw_apply_single_kernel<V><<<(unsigned)blocks, threads, 0, stream>>>(idx, dd, dist_is_squared, M, k_table,
-                                                                            k_use, k_min, power, vals, n_samples,
-                                                                            stride_i, out);
+        idw_apply_single_kernel<V, false><<<(unsigned)blocks, threads, 0, stream>>>(
+            idx, dd, dist_is_squared, M, k_table, k_use, k_min, power, vals, n_samples, stride_i, out, nullptr, nullptr);
         note_launch();
         return check_launch();
     }
@@ -592,8 +660,10 @@ int idw_entry(const double* s_lat, const double* s_lon, int64_t n, const V* vals
 #endif
     // Short batches with the cell-binned search: the weighting is applied inside the search kernel (fused batch
     // epilogue, knn.cu finish_batch) - the [M][k] table is never written or read back.  Long batches amortise the table
-    // and use the neighbour-sharing K2 kernel; the brute-force kernel K1 keeps the table path.
-    if (search != CMX_SEARCH_BRUTE && layout == CMX_LAYOUT_SAMPLE_MAJOR && n_batch < CMX_K2_UNION_MIN_BATCH && M > 0) {
+    // and use the neighbour-sharing K2 kernel; the brute-force kernel K1 keeps the table path.  So does a sharded call
+    // that stores into several ranks: the fused epilogue finishes 4 targets at a time, i.e. 32-byte segments per peer,
+    // and NVLink wants K2's 128/256-byte ones (8 GPUs, C5 band: 15.7 ms fused against 1.7 + 2.5 ms through the table).
+    if (search != CMX_SEARCH_BRUTE && layout == CMX_LAYOUT_SAMPLE_MAJOR && n_batch < CMX_K2_UNION_MIN_BATCH && M > 0 && po.n <= 1) {
         CMX_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), stream));
         flag_nonfinite_kernel<V><<<sm_count() * 8, 256, 0, stream>>>(vals, (long long)n * n_batch, flag);
         note_launch();
@@ -638,10 +708,66 @@ int apply_entry(const int32_t* idx, const double* dist, int64_t M, int k_table, 
                              flag_scratch, stream, po);
 }
 
+inline long long idw_score_ctas(long long M) { return (M * 32 + 255) / 256; }
+
+template <typename V>
+int idw_score_entry(const int32_t* idx, const double* dist, int64_t M, int k_table, const V* vals, int64_t n, int k_use,
+                    int k_min, double power, const V* truth, V* out, double* sums, void* ws, size_t ws_bytes, void* stream_) {
+    if (!idx || !dist || !vals || !truth || !sums || !ws) return CMX_ERR_BAD_ARG;
+    if (M < 1 || k_use < 1 || k_use > k_table || k_min < 1) return CMX_ERR_BAD_ARG;
+    if (k_use > CMX_MAX_K) return CMX_ERR_K_TOO_LARGE;
+    const long long ctas = idw_score_ctas(M);
+    if (ws_bytes < (size_t)ctas * 3 * sizeof(double)) return CMX_ERR_WORKSPACE;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    double* part = static_cast<double*>(ws);
+    idw_apply_single_kernel<V, true><<<(unsigned)ctas, 256, 0, stream>>>(idx, dist, 0, M, k_table, k_use, k_min, power, vals, n,
+                                                                        1, out, truth, part);
+    note_launch();
+    score_reduce_kernel<<<1, 256, 0, stream>>>(part, ctas, sums);
+    note_launch();
+    return check_launch();
+}
+
+template <typename V>
+int score_entry(const V* pred, const V* truth, int64_t n, double* sums, void* ws, size_t ws_bytes, void* stream_) {
+    if (!pred || !truth || !sums || !ws || n < 1) return CMX_ERR_BAD_ARG;
+    if (ws_bytes < (size_t)SCORE_CTAS * 3 * sizeof(double)) return CMX_ERR_WORKSPACE;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    double* part = static_cast<double*>(ws);
+    long long ctas = (n + 255) / 256;
+    if (ctas > SCORE_CTAS) ctas = SCORE_CTAS;
+    score_kernel<V><<<(unsigned)ctas, 256, 0, stream>>>(pred, truth, n, part);
+    note_launch();
+    score_reduce_kernel<<<1, 256, 0, stream>>>(part, ctas, sums);
+    note_launch();
+    return check_launch();
+}
+
 }  // namespace
 }  // namespace cmx
 
 extern "C" {
+
+size_t cmx_score_workspace_bytes(int64_t n_targets) {
+    const long long a = cmx::idw_score_ctas(n_targets > 0 ? n_targets : 0), b = cmx::SCORE_CTAS;
+    return (size_t)(a > b ? a : b) * 3 * sizeof(double);
+}
+int cmx_idw_score_f64(const int32_t* idx, const double* dist, int64_t M, int k_table, const double* vals, int64_t n, int k_use,
+                      int k_min, double power, const double* truth, double* out, double* sums, void* ws, size_t ws_bytes,
+                      void* stream) {
+    return cmx::idw_score_entry<double>(idx, dist, M, k_table, vals, n, k_use, k_min, power, truth, out, sums, ws, ws_bytes, stream);
+}
+int cmx_idw_score_f32(const int32_t* idx, const double* dist, int64_t M, int k_table, const float* vals, int64_t n, int k_use,
+                      int k_min, double power, const float* truth, float* out, double* sums, void* ws, size_t ws_bytes,
+                      void* stream) {
+    return cmx::idw_score_entry<float>(idx, dist, M, k_table, vals, n, k_use, k_min, power, truth, out, sums, ws, ws_bytes, stream);
+}
+int cmx_score_f64(const double* pred, const double* truth, int64_t n, double* sums, void* ws, size_t ws_bytes, void* stream) {
+    return cmx::score_entry<double>(pred, truth, n, sums, ws, ws_bytes, stream);
+}
+int cmx_score_f32(const float* pred, const float* truth, int64_t n, double* sums, void* ws, size_t ws_bytes, void* stream) {
+    return cmx::score_entry<float>(pred, truth, n, sums, ws, ws_bytes, stream);
+}
 
 size_t cmx_idw_workspace_bytes(int k, int64_t n_targets, int64_t n_batch) {
     if (n_batch <= 1 || k < 1 || n_targets < 0) return 0;

@@ -357,6 +357,56 @@ def idw_apply(idx: torch.Tensor, dist: torch.Tensor, values, *, k: int | None = 
     return out
 
 
+def _score_from_sums(sums: torch.Tensor) -> dict:
+    s_abs, s_sq, count = (float(v) for v in sums.cpu())
+    if count == 0:
+        return {"mae": float("nan"), "mse": float("nan"), "rmse": float("nan"), "count": 0}
+    mse = s_sq / count
+    return {"mae": s_abs / count, "mse": mse, "rmse": float(np.sqrt(mse)), "count": int(count)}
+
+
+def idw_score(idx: torch.Tensor, dist: torch.Tensor, values: torch.Tensor, truth: torch.Tensor, *, k: int | None = None,
+              power: float = 2.0, k_min: int = 2, return_field: bool = False):
+    """One hyper-parameter trial of IDW on a stored neighbour table, scored against held-out values in the same
+    kernel (reference: optim/bayesian.py:399-408 -> comparison.py:268-306, nanmean of |d| and d^2).  The field is
+    not written unless ``return_field``.  Returns ``{"mae", "mse", "rmse", "count"}`` (and the field)."""
+    lib = _lib.load()
+    dev = _require_cuda(idx.device)
+    m, k_table = idx.shape
+    k = k_table if k is None else int(k)
+    dtype = values.dtype
+    if dtype not in (torch.float64, torch.float32) or truth.dtype != dtype:
+        raise TypeError("values and truth must share a float32 or float64 dtype")
+    if truth.numel() != m:
+        raise ValueError("truth must hold one value per target")
+    with torch.cuda.device(dev):
+        sums = torch.empty(3, dtype=torch.float64, device=dev)
+        out = torch.empty(m, dtype=dtype, device=dev) if return_field else None
+        ws = _workspace(lib.cmx_score_workspace_bytes(m), dev)
+        fn = lib.cmx_idw_score_f64 if dtype == torch.float64 else lib.cmx_idw_score_f32
+        rc = fn(_ptr(idx.contiguous()), _ptr(dist.contiguous()), m, k_table, _ptr(values.contiguous()), values.numel(), k,
+                int(k_min), float(power), _ptr(truth.contiguous()), _ptr(out), _ptr(sums), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "cmx_idw_score")
+    score = _score_from_sums(sums)
+    return (score, out) if return_field else score
+
+
+def score(pred: torch.Tensor, truth: torch.Tensor) -> dict:
+    """NaN-aware MAE / MSE / RMSE of a device field against held-out values (comparison.py:268-306), reduced on the
+    device in a fixed order."""
+    lib = _lib.load()
+    dev = _require_cuda(pred.device)
+    if pred.dtype not in (torch.float64, torch.float32) or truth.dtype != pred.dtype or truth.numel() != pred.numel():
+        raise TypeError("pred and truth must have the same float32/float64 dtype and size")
+    with torch.cuda.device(dev):
+        sums = torch.empty(3, dtype=torch.float64, device=dev)
+        ws = _workspace(lib.cmx_score_workspace_bytes(pred.numel()), dev)
+        fn = lib.cmx_score_f64 if pred.dtype == torch.float64 else lib.cmx_score_f32
+        rc = fn(_ptr(pred.contiguous()), _ptr(truth.contiguous()), pred.numel(), _ptr(sums), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "cmx_score")
+    return _score_from_sums(sums)
+
+
 def empirical_variogram(x, y, z, nlags: int, *, geographic: bool = False, group=None):
     """pykrige ``_initialize_variogram_model`` binning on the device.
 

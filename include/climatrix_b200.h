@@ -15,6 +15,7 @@
  *                         src/climatrix/reconstruct/idw.py:155-180
  *   cmx_idw_apply_*    <- idw.py:163-180 re-applied to a stored neighbour table
  *                         (HPO inner loop, src/climatrix/optim/bayesian.py:399-405)
+ *   cmx_idw_score_*, cmx_score_* <- one HPO trial's score: bayesian.py:399-408 + comparison.py:268-306
  *   cmx_variogram_*    <- pykrige core._initialize_variogram_model (pdist + binning),
  *                         reached from src/climatrix/reconstruct/kriging.py:215-224
  *   cmx_ok_mw_f64/_f32 <- pykrige OrdinaryKriging.execute(backend="loop",
@@ -182,6 +183,31 @@ int cmx_idw_apply_f32(const int32_t* idx, const double* dist, int64_t n_targets,
                       const float* vals, int64_t n_samples, int64_t n_batch, int vals_layout,
                       int k_use, int k_min, double power, float* out, int32_t* flag_scratch,
                       const cmx_options* options, void* stream);
+
+/*
+ * Score of one hyper-parameter trial against held-out values: the loop body of climatrix's HParamFinder,
+ * src/climatrix/optim/bayesian.py:380-425 (reconstruct train -> val.domain, then Comparison.compute) with the
+ * metrics of src/climatrix/comparison.py:268-306 (nanmean of |d|, d^2 over d = predicted - true).
+ *   sums (device, 3 doubles): sum |d|, sum d^2, number of targets where prediction and truth are both finite;
+ *                              MAE = sums[0]/sums[2], MSE = sums[1]/sums[2], RMSE = sqrt(MSE).
+ *   cmx_idw_score_*: weighting of a stored neighbour table (as cmx_idw_apply_*, one slice) with the error reduction
+ *                    fused into the same kernel; `out` may be NULL - the field is then never written.
+ *   cmx_score_*:     the reduction alone, for a field that exists (ordinary-kriging trials).
+ * workspace: cmx_score_workspace_bytes(n_targets).  Deterministic (fixed partial slots, fixed order).
+ */
+size_t cmx_score_workspace_bytes(int64_t n_targets);
+int cmx_idw_score_f64(const int32_t* idx, const double* dist, int64_t n_targets, int k_table,
+                      const double* vals, int64_t n_samples, int k_use, int k_min, double power,
+                      const double* truth, double* out, double* sums,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int cmx_idw_score_f32(const int32_t* idx, const double* dist, int64_t n_targets, int k_table,
+                      const float* vals, int64_t n_samples, int k_use, int k_min, double power,
+                      const float* truth, float* out, double* sums,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int cmx_score_f64(const double* pred, const double* truth, int64_t n, double* sums,
+                  void* workspace, size_t workspace_bytes, void* stream);
+int cmx_score_f32(const float* pred, const float* truth, int64_t n, double* sums,
+                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- empirical variogram (pykrige core._initialize_variogram_model) ---- */
 

@@ -317,6 +317,66 @@ def test_hyperparameter_search_inner_loop_matches_per_trial_reconstructions():
         search.score(51)
 
 
+def test_fused_idw_score_equals_field_then_reduce_with_nan_handling():
+    """cmx_idw_score_*: the fused kernel's sums equal the separate field + NumPy nanmean, NaNs in the field (k_min rule)
+    and in the truth are skipped like comparison.py:268-306, and the optional field output equals cmx_idw_apply_*."""
+    la, lo, v, rng = _samples(4000, 77)
+    v = v.copy()
+    v[rng.choice(4000, 600, replace=False)] = np.nan
+    tl, to = rng.uniform(-60, 60, 2500), rng.uniform(-170, 170, 2500)
+    truth = np.cos(np.deg2rad(tl)) * 10 + rng.normal(size=2500)
+    truth[::37] = np.nan
+    T = K.Targets.make(tl, to, False, DEV)
+    dist, idx = K.knn(la, lo, T, 24)
+    for dt, tol in ((torch.float64, 1e-12), (torch.float32, 1e-5)):
+        vals = torch.as_tensor(v).to(DEV, dt)
+        tr = torch.as_tensor(truth).to(DEV, dt)
+        field = K.idw_apply(idx, dist, vals, k=17, power=1.7, k_min=15, dtype=dt)
+        assert torch.isnan(field).any() and not torch.isnan(field).all()
+        got, out = K.idw_score(idx, dist, vals, tr, k=17, power=1.7, k_min=15, return_field=True)
+        assert torch.equal(torch.nan_to_num(out, nan=-7.0), torch.nan_to_num(field, nan=-7.0))
+        d = field.double().cpu().numpy() - tr.double().cpu().numpy()
+        assert got["count"] == int(np.isfinite(d).sum())
+        assert abs(got["mae"] - np.nanmean(np.abs(d))) <= tol * 10
+        assert abs(got["rmse"] - np.sqrt(np.nanmean(d * d))) <= tol * 10
+        assert K.idw_score(idx, dist, vals, tr, k=17, power=1.7, k_min=15) == got        # no field written: same sums
+        alone = K.score(field, tr)
+        assert alone["count"] == got["count"] and abs(alone["mae"] - got["mae"]) <= tol and abs(alone["mse"] - got["mse"]) <= tol * 10
+    big = torch.as_tensor(rng.normal(size=3_000_001)).to(DEV)                               # more targets than score CTAs
+    ref = torch.as_tensor(rng.normal(size=3_000_001)).to(DEV)
+    s = K.score(big, ref)
+    dd = (big - ref).cpu().numpy()
+    assert s["count"] == dd.size and abs(s["mae"] - np.abs(dd).mean()) <= 1e-12 and abs(s["mse"] - (dd * dd).mean()) <= 1e-12
+    assert K.score(big, ref) == s                                                           # deterministic
+
+
+def test_ok_search_matches_per_trial_reconstructions():
+    """OKSearch (kriging half): cached frames / variograms give the same scores as one
+    OrdinaryKrigingReconstructor per trial followed by comparison.py's nanmean metrics."""
+    from climatrix_b200.hpo import OKSearch
+
+    la, lo, v, rng = _samples(1200, 91)
+    keep = rng.random(1200) < 0.7
+    train = static_sparse(la[keep], lo[keep], v[keep])
+    val = static_sparse(la[~keep], lo[~keep], v[~keep])
+    search = OKSearch(train, val, n_closest_points=16)
+    trials = [dict(nlags=6, anisotropy_scaling=1.0, variogram_model="spherical"),
+              dict(nlags=6, anisotropy_scaling=1.0, variogram_model="exponential"),      # cached frame + variogram
+              dict(nlags=9, anisotropy_scaling=1.0, variogram_model="linear"),           # cached frame
+              dict(nlags=6, anisotropy_scaling=2.5, variogram_model="gaussian"),
+              dict(nlags=6, anisotropy_scaling=1.0, coordinates_type="geographic", variogram_model="spherical")]
+    for kw in trials:
+        ref = cm.OrdinaryKrigingReconstructor(train, val.domain, n_closest_points=16, **kw).reconstruct().da.values
+        d = np.asarray(ref).reshape(-1) - v[~keep]
+        assert abs(search.score(metric="mae", **kw) - np.nanmean(np.abs(d))) <= 1e-8 * max(1.0, np.nanmean(np.abs(d)))
+        assert abs(search.score(metric="rmse", **kw) - np.sqrt(np.nanmean(d * d))) <= 1e-8 * max(1.0, np.sqrt(np.nanmean(d * d)))
+    assert len(search._frames) == 3 and len(search._variograms) == 4
+    glob = OKSearch(train, val, n_closest_points=None)
+    ref = cm.OrdinaryKrigingReconstructor(train, val.domain, nlags=6, anisotropy_scaling=1.0, variogram_model="spherical").reconstruct().da.values
+    d = np.asarray(ref).reshape(-1) - v[~keep]
+    assert abs(glob.score(nlags=6, anisotropy_scaling=1.0, variogram_model="spherical", metric="mae") - np.nanmean(np.abs(d))) <= 1e-8
+
+
 def test_reference_interface_combinations_return_the_right_kind():
     """The four sparse/dense x sparse/dense cases of test_base_interface.py:235-279 (k=5 == N)."""
     sp, de = sparse_dataset(), dense_dataset()

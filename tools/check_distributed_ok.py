@@ -24,10 +24,13 @@ a = cm.OrdinaryKrigingReconstructor(src, tgt, **kw)
 one = a.reconstruct().da.values
 b = cm.OrdinaryKrigingReconstructor(src, tgt, group=dist.group.WORLD, **kw)
 many = b.reconstruct().da.values
-# the pair-sharded variogram sums in a different order: parameters agree to rounding, fields to ~1e-12
-np.testing.assert_allclose(b.variogram_model_parameters, a.variogram_model_parameters, rtol=1e-9, atol=1e-12)
+# The pair-sharded variogram adds the ranks' partial sums in a different order than one GPU does: the semivariances
+# differ in the last bit, and the fit (finite-difference Jacobian, stops at ftol = 1e-8) moves the parameters by up to
+# ~1e-7 relative.  Two ranks happen to reproduce the single-rank sums bit for bit; eight do not.
+perr = np.max(np.abs(b.variogram_model_parameters - a.variogram_model_parameters) / np.maximum(np.abs(a.variogram_model_parameters), 1e-6))
 err = np.max(np.abs(many - one)) / np.max(np.abs(one))
 errv = np.max(np.abs(b.variance_ - a.variance_)) / np.max(np.abs(a.variance_))
-assert err <= 1e-9 and errv <= 1e-9, (err, errv)
+print(f"rank {rank}: parameters differ by {perr:.2e}, field {err:.2e}, variance {errv:.2e}", flush=True)
+assert perr <= 1e-5 and err <= 1e-6 and errv <= 1e-6, (perr, err, errv)
 print(f"rank {rank}/{world}: distributed OK matches the single-rank field (max rel diff {err:.2e}, variance {errv:.2e})")
 dist.destroy_process_group()
