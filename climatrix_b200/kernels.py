@@ -598,7 +598,7 @@ def ok_global(s_x, s_y, z, t_x, t_y, grid: bool, *, variogram_model: str, params
 
     One solve of the (N+1) x (N+1) system serves every target (``csrc/global_kriging.cu``: blocked Cholesky of the
     shifted positive-definite matrix; ``pseudo_inv`` or a numerically singular matrix -> one-sided Jacobi SVD, N <= 4095).
-    Coordinates in the kriging frame.  Returns ``(field (M,), status)`` with status 0 = Cholesky, 1 = SVD fallback,
+    Coordinates in the kriging frame.  Returns ``(field (M,), status)`` with status 0 = the requested path ran, 1 = SVD fallback after a failed Cholesky,
     2 = numerically singular and too large for the SVD path (field undefined).
     """
     lib = _lib.load()

@@ -329,7 +329,8 @@ int cmx_ok_solve_f32(const double* s_x, const double* s_y, const double* z, int6
  * when pseudo_inv is requested).
  * Coordinates in the kriging frame like cmx_ok_mw_*; metric CMX_METRIC_GEOGRAPHIC uses great-circle distances.
  * *status (HOST int, may be NULL; the call synchronises the stream once to read the factorisation flag):
- *   0 Cholesky path, 1 fell back to the SVD path, 2 numerically singular and too large for the SVD path (out untouched).
+ *   0 the requested path ran (Cholesky, or the SVD when pseudo_inv != 0), 1 the Cholesky met a non-positive pivot and the
+ *   call fell back to the SVD path, 2 numerically singular and too large for the SVD path (out untouched).
  */
 size_t cmx_ok_global_workspace_bytes(int64_t n_samples);
 int cmx_ok_global_f64(const double* s_x, const double* s_y, const double* z, int64_t n_samples,

@@ -377,6 +377,38 @@ def test_ok_search_matches_per_trial_reconstructions():
     assert abs(glob.score(nlags=6, anisotropy_scaling=1.0, variogram_model="spherical", metric="mae") - np.nanmean(np.abs(d))) <= 1e-8
 
 
+def test_kriging_kernels_match_the_hand_derived_fixture():
+    """K4 (Cholesky and pivoted solvers) and K5 against tests/golden/ok_hand_derived.json - kriging systems on a 3-4-5
+    lattice solved in exact rational arithmetic (oracle/make_hand_fixture.py), independent of pykrige_restated.py.
+    Includes exact hits (weight 1 on the coincident sample, zero variance)."""
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ok_hand_derived.json")) as f:
+        cases = json.load(f)["cases"]
+    for case in cases:
+        x, y, z = (np.array(case[key]) for key in ("x", "y", "values"))
+        tx = np.array([t["target"][0] for t in case["targets"]])
+        ty = np.array([t["target"][1] for t in case["targets"]])
+        want_z = np.array([t["z"] for t in case["targets"]])
+        want_s = np.array([t["sigmasq"] for t in case["targets"]])
+        kw = dict(variogram_model="linear", params=case["variogram_parameters"])
+        xs, ys = torch.as_tensor(x).to(DEV), torch.as_tensor(y).to(DEV)
+        out, sig, nsing = K.ok_moving_window(xs, ys, z, tx, ty, False, k=len(x), return_sigmasq=True, **kw)
+        assert int(nsing.item()) == 0
+        np.testing.assert_allclose(out.cpu().numpy(), want_z, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(sig.cpu().numpy(), want_s, rtol=0, atol=1e-12)
+        dist, idx = K.knn(ys, xs, K.Targets.make(ty, tx, False, DEV), len(x))
+        for solver in ("auto", "pivoted"):
+            out, sig, nsing = K.ok_solve(xs, ys, z, idx, dist * dist, return_sigmasq=True, solver=solver, **kw)
+            np.testing.assert_allclose(out.cpu().numpy(), want_z, rtol=0, atol=1e-12)
+            np.testing.assert_allclose(sig.cpu().numpy(), want_s, rtol=0, atol=1e-12)
+        for pinv in (False, True):
+            out, status = K.ok_global(xs, ys, z, tx, ty, False, pseudo_inv=pinv, **kw)
+            assert status == 0, (case["name"], pinv, status)   # the requested path ran, no fallback
+            np.testing.assert_allclose(out.cpu().numpy(), want_z, rtol=0, atol=1e-12)
+
+
 def test_reference_interface_combinations_return_the_right_kind():
     """The four sparse/dense x sparse/dense cases of test_base_interface.py:235-279 (k=5 == N)."""
     sp, de = sparse_dataset(), dense_dataset()

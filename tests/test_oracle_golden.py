@@ -77,3 +77,34 @@ def test_kriging_oracle_self_checks():
     # constant + tiny noise stays near the constant (weights sum to one)
     c = ok_oracle(lat, lon, 5.0 + 1e-9 * rng.normal(size=120), t_lat, t_lon, False, n_closest_points=8, **kw)
     np.testing.assert_allclose(c, 5.0, atol=1e-6)
+
+
+def _hand_cases():
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ok_hand_derived.json")) as f:
+        return json.load(f)["cases"]
+
+
+def test_restated_pykrige_matches_the_hand_derived_fixture():
+    """tests/golden/ok_hand_derived.json was solved in exact rational arithmetic (oracle/make_hand_fixture.py) and does
+    not pass through pykrige_restated.py: the restatement - global and moving-window execute() - must reproduce it."""
+    from oracle import pykrige_restated as pk
+    from oracle.ok_oracle import moving_window_with_parameters
+
+    for case in _hand_cases():
+        x, y, z = (np.array(case[key]) for key in ("x", "y", "values"))
+        tx = np.array([t["target"][0] for t in case["targets"]])
+        ty = np.array([t["target"][1] for t in case["targets"]])
+        want_z = np.array([t["z"] for t in case["targets"]])
+        want_s = np.array([t["sigmasq"] for t in case["targets"]])
+        okr = pk.OrdinaryKriging(x, y, z, variogram_model="linear", variogram_parameters=case["variogram_parameters"])
+        for backend in ("vectorized", "loop"):
+            got_z, got_s = okr.execute("points", tx, ty, backend=backend)
+            np.testing.assert_allclose(got_z, want_z, rtol=0, atol=1e-13)
+            np.testing.assert_allclose(got_s, want_s, rtol=0, atol=1e-13)
+        got_z, got_s = moving_window_with_parameters(x, y, z, tx, ty, "points", k=len(x), variogram_model="linear",
+                                                     parameters=case["variogram_parameters"])
+        np.testing.assert_allclose(got_z, want_z, rtol=0, atol=1e-13)
+        np.testing.assert_allclose(got_s, want_s, rtol=0, atol=1e-13)
