@@ -29,7 +29,7 @@ from typing import ClassVar, Literal
 import numpy as np
 
 from .dataset import BaseClimatrixDataset, Domain
-from .exceptions import OperationNotSupportedForDynamicDatasetError
+from .exceptions import OperationNotSupportedForDynamicDatasetError, ReconstructorConfigurationFailed
 from .idw import extra_dimensions
 from .plugin import BaseReconstructor, Hyperparameter
 
@@ -110,7 +110,8 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
     dataset : BaseClimatrixDataset  (sparse source only, as in the reference)
     target_domain : Domain
     backend : "vectorized" | "loop" | None   kept for compatibility (global mode picks like the reference)
-    nlags : int, default 6
+    nlags : int, default 6             (1..64: the device binning keeps at most 64 lag bins; the reference's
+                                       search range is 4..20, pykrige itself has no limit)
     anisotropy_scaling : float, default 1e-6
     coordinates_type : "euclidean" | "geographic", default "euclidean"
     variogram_model : "linear" | "power" | "gaussian" | "spherical" | "exponential", default "linear"
@@ -164,6 +165,8 @@ class OrdinaryKrigingReconstructor(BaseReconstructor):
             self.dataset = self.dataset.to_positive_longitude()  # a no-op for sparse sources (base.py:227-231)
         self.backend = backend
         self.nlags = nlags or self.nlags
+        if not 1 <= int(self.nlags) <= 64:
+            raise ReconstructorConfigurationFailed("nlags must be between 1 and 64 (device binning limit)")
         self.anisotropy_scaling = anisotropy_scaling or self.anisotropy_scaling
         self.coordinates_type = coordinates_type or self.coordinates_type
         self.variogram_model = variogram_model or self.variogram_model

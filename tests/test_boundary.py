@@ -286,3 +286,19 @@ def test_product_code_does_not_import_the_oracle():
             if f.endswith(".py"):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_ok_rejects_nlags_beyond_the_device_binning_limit():
+    """The device variogram keeps at most 64 lag bins (the reference searches 4..20; pykrige has no limit): the
+    constructor says so instead of failing later with NotImplementedError."""
+    import climatrix_b200 as cm
+    from climatrix_b200.exceptions import ReconstructorConfigurationFailed
+
+    rng = np.random.default_rng(0)
+    n = 50
+    lat, lon = rng.uniform(-50, 50, n), rng.uniform(-100, 100, n)
+    src = cm.BaseClimatrixDataset(cm.FieldArray(rng.normal(size=n), ("point",), {"point": np.arange(n), "latitude": (("point",), lat), "longitude": (("point",), lon)}))
+    tgt = cm.Domain.from_lat_lon(np.linspace(-40, 40, 5), np.linspace(-90, 90, 7), kind="dense")
+    with pytest.raises(ReconstructorConfigurationFailed):
+        cm.OrdinaryKrigingReconstructor(src, tgt, nlags=65)
+    cm.OrdinaryKrigingReconstructor(src, tgt, nlags=64)
