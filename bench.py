@@ -577,7 +577,10 @@ class Runner:
     def config(self, name):
         method, n, n_lat, n_lon, t, k, desc = WORKLOADS[name]
         return {"workload": f"{name}: {desc}", "samples": n, "targets": n_lat * n_lon, "batch": t, "k": k,
-                "method": method, "sharding": f"target rows over {max(self.world, 1)} rank(s), samples replicated",
+                "method": method,
+                "sharding": (f"none: {n_lat * n_lon} windows of k={k} are too small to shard (sharding.OK_SHARD_MIN_WORK), every one of the "
+                             f"{self.world} ranks solves the whole field" if method == "ok" and self.world > 1 and n_lat * n_lon * k * k < 2.0e8
+                             else f"target rows over {max(self.world, 1)} rank(s), samples replicated"),
                 "l2": "per-step working set (samples+values+output) exceeds the 126 MB L2; no explicit flush"
                       if name in ("c3", "c4", "c5") else "working set fits the 126 MB L2 (latency-bound configuration); no explicit flush"}
 
