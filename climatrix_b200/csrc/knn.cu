@@ -1085,9 +1085,16 @@ __device__ __forceinline__ double seed_bound_d2_warp(const SeedGrid& s, const in
 // running k-th distance go through the same bitonic sort / merge network as K1's re-rank.  The order of the
 // samples inside a cell (atomics in the scatter) cannot change the result: the list is the lexicographic
 // (d2, index) top-k of a candidate set that always contains the true top-k.
+// Chain: the previous target this warp searched (coordinates pa, pb; exact k-th squared distance pk, inf = none).
+// Every one of its k neighbours lies within d_k(prev) + |prev - target| of this target (triangle inequality), so that
+// sum bounds this target's k-th distance - for adjacent grid points a tighter start than the summed-area-table box,
+// and it costs three flops instead of a table walk.  Used when the step is at most half of d_k(prev).
+struct SearchChain {
+    double pa, pb, pk;
+};
 template <int E>
 __device__ __forceinline__ void binned_search_target(const KnnArgs& a, const SeedGrid& s, const int* __restrict__ sat, int k,
-                                                     int lane, long long m, double (&ld)[E], int (&li)[E]) {
+                                                     int lane, long long m, double (&ld)[E], int (&li)[E], SearchChain& ch) {
     double ta, tb;
     if (a.j.grid) {
         const long long row = m / a.j.n_b;
@@ -1106,7 +1113,14 @@ __device__ __forceinline__ void binned_search_target(const KnnArgs& a, const See
     double kth = CMX_INF;
     bool empty = true;
     if (s.valid) {
-        kth = seed_bound_d2_warp(s, sat, ta, tb, k, lane);
+        const double sa = ta - ch.pa, sb = tb - ch.pb;
+        const double step2 = sa * sa + sb * sb;
+        if (ch.pk < CMX_INF && step2 <= 0.25 * ch.pk) {  // (false for NaN steps and an unset chain)
+            const double D = (sqrt(ch.pk) + sqrt(step2)) * (1.0 + 1e-12);
+            kth = D * D * (1.0 + 1e-12);
+        } else {
+            kth = seed_bound_d2_warp(s, sat, ta, tb, k, lane);
+        }
         if (kth < CMX_INF) {
             const double D = sqrt(kth) * (1.0 + 1e-12);
             ra0 = seed_cell(ta - D, s.a0, s.inv_h, s.ga);
@@ -1173,6 +1187,15 @@ __device__ __forceinline__ void binned_search_target(const KnnArgs& a, const See
             }
         }
     }
+    {   // hand the exact k-th distance to the next target of this warp
+        double sel = ld[0];
+#pragma unroll
+        for (int e = 1; e < E; ++e)
+            if (((k - 1) >> 5) == e) sel = ld[e];
+        ch.pa = ta;
+        ch.pb = tb;
+        ch.pk = __shfl_sync(kFull, sel, (k - 1) & 31);  // inf when the list holds fewer than k samples
+    }
 }
 
 // P = 0: neighbour table and / or the single-slice IDW epilogue.  P = 2, 4: short time / level batches (up to P * 32
@@ -1189,13 +1212,16 @@ __global__ void __launch_bounds__(256) knn_binned_kernel(const __grid_constant__
     // (the batch epilogue's value-row gathers hit L1 instead of L2).
     const int CHUNK = a.chunk;  // units (targets, or groups of four targets) per CTA and chunk; a multiple of 8
     const int wib = threadIdx.x >> 5;
+    const int per_warp = CHUNK >> 3;  // every warp takes a run of CONSECUTIVE units of the chunk (see SearchChain)
+    SearchChain chain{0.0, 0.0, CMX_INF};
     if constexpr (P == 0) {
         for (long long base = (long long)blockIdx.x * CHUNK; base < a.M; base += (long long)gridDim.x * CHUNK) {
-            const long long end = base + CHUNK < a.M ? base + CHUNK : a.M;
-            for (long long m = base + wib; m < end; m += 8) {
+            const long long first = base + (long long)wib * per_warp;
+            const long long end = first + per_warp < a.M ? first + per_warp : a.M;
+            for (long long m = first; m < end; ++m) {
                 double ld[E];
                 int li[E];
-                binned_search_target<E>(a, s, sat, k, lane, m, ld, li);
+                binned_search_target<E>(a, s, sat, k, lane, m, ld, li, chain);
                 const double r = finish_target<E>(a, lane, m, ld, li);
                 if (a.j.idw_mode == 1 && lane == 0) {
                     if (a.j.value_is_f32)
@@ -1214,7 +1240,8 @@ __global__ void __launch_bounds__(256) knn_binned_kernel(const __grid_constant__
         const bool tables = a.j.idx_out || a.j.dist_out || a.j.d2_out;
         const long long groups = (a.M + G - 1) / G;
         for (long long base = (long long)blockIdx.x * CHUNK; base < groups; base += (long long)gridDim.x * CHUNK)
-        for (long long g = base + wib; g < (base + CHUNK < groups ? base + CHUNK : groups); g += 8) {
+        for (long long g = base + (long long)wib * per_warp;
+             g < (base + (long long)(wib + 1) * per_warp < groups ? base + (long long)(wib + 1) * per_warp : groups); ++g) {
             const long long m0 = g * G;
             const int count = (int)(a.M - m0 < G ? a.M - m0 : G);
             // a run-time loop: ONE copy of the search + epilogue code (four inlined copies overflow the instruction
@@ -1223,7 +1250,7 @@ __global__ void __launch_bounds__(256) knn_binned_kernel(const __grid_constant__
             for (int q = 0; q < count; ++q) {
                 double ld[E];
                 int li[E];
-                binned_search_target<E>(a, s, sat, k, lane, m0 + q, ld, li);
+                binned_search_target<E>(a, s, sat, k, lane, m0 + q, ld, li, chain);
                 if (tables) finish_target<E>(a, lane, m0 + q, ld, li);
                 double r[P];
                 finish_batch<E, P>(a, lane, ld, li, strip, r);
