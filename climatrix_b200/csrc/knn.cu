@@ -103,7 +103,8 @@ struct KnnArgs {
     double* bin_a;       // [N] sorted copies of the sample coordinates
     double* bin_b;
     int* bin_idx;        // [N] original sample index of each sorted slot
-    int chunk;           // K1c: consecutive work units (targets / four-target groups) a CTA takes at a time
+    int chunk;
+    int run;             // consecutive units a warp takes before it strides on (binned search: chained bound vs L1 reuse)           // K1c: consecutive work units (targets / four-target groups) a CTA takes at a time
 };
 
 // ------------------------------------------------------------------------------------------
@@ -1212,13 +1213,15 @@ __global__ void __launch_bounds__(256) knn_binned_kernel(const __grid_constant__
     // (the batch epilogue's value-row gathers hit L1 instead of L2).
     const int CHUNK = a.chunk;  // units (targets, or groups of four targets) per CTA and chunk; a multiple of 8
     const int wib = threadIdx.x >> 5;
-    const int per_warp = CHUNK >> 3;  // every warp takes a run of CONSECUTIVE units of the chunk (see SearchChain)
+    // A warp takes RUN consecutive units, then strides over the other warps' runs: consecutive targets feed the chained
+    // bound (SearchChain), while the 8 warps of the CTA stay on neighbouring targets so that they share L1 lines.
+    const int RUN = a.run;
     SearchChain chain{0.0, 0.0, CMX_INF};
     if constexpr (P == 0) {
         for (long long base = (long long)blockIdx.x * CHUNK; base < a.M; base += (long long)gridDim.x * CHUNK) {
-            const long long first = base + (long long)wib * per_warp;
-            const long long end = first + per_warp < a.M ? first + per_warp : a.M;
-            for (long long m = first; m < end; ++m) {
+            const long long cend = base + CHUNK < a.M ? base + CHUNK : a.M;
+            for (long long first = base + (long long)wib * RUN; first < cend; first += 8LL * RUN)
+            for (long long m = first; m < (first + RUN < cend ? first + RUN : cend); ++m) {
                 double ld[E];
                 int li[E];
                 binned_search_target<E>(a, s, sat, k, lane, m, ld, li, chain);
@@ -1240,8 +1243,8 @@ __global__ void __launch_bounds__(256) knn_binned_kernel(const __grid_constant__
         const bool tables = a.j.idx_out || a.j.dist_out || a.j.d2_out;
         const long long groups = (a.M + G - 1) / G;
         for (long long base = (long long)blockIdx.x * CHUNK; base < groups; base += (long long)gridDim.x * CHUNK)
-        for (long long g = base + (long long)wib * per_warp;
-             g < (base + (long long)(wib + 1) * per_warp < groups ? base + (long long)(wib + 1) * per_warp : groups); ++g) {
+        for (long long first = base + (long long)wib * RUN; first < (base + CHUNK < groups ? base + CHUNK : groups); first += 8LL * RUN)
+        for (long long g = first; g < first + RUN && g < base + CHUNK && g < groups; ++g) {
             const long long m0 = g * G;
             const int count = (int)(a.M - m0 < G ? a.M - m0 : G);
             // a run-time loop: ONE copy of the search + epilogue code (four inlined copies overflow the instruction
@@ -1276,6 +1279,9 @@ int launch_binned(const KnnArgs& args_, bool scatter, cudaStream_t stream) {
     {   // chunks of 64 units when that still gives every CTA slot work, else the finest split (8 = one unit per warp)
         const long long units = args.j.idw_mode == 2 ? (args.M + 3) / 4 : args.M;
         args.chunk = units >= 64LL * sms * 8 ? 64 : (units >= 16LL * sms * 8 ? 16 : 8);
+        args.run = args.chunk / 8;
+        if (const char* e = getenv("CMX_K1C_RUN")) args.run = atoi(e);
+        if (args.run < 1) args.run = 1;
     }
     timing_begin(CMX_KERNEL_KNN_BINNED, stream);
     if (scatter) {  // (small sample sets: already done by seed_small_kernel; the cursors were cleared by the pre-pass)

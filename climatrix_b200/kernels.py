@@ -92,6 +92,43 @@ def _as_f64(x, device) -> torch.Tensor:
     return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).to(device, non_blocking=True)
 
 
+_staging: dict = {}
+UPLOAD_CHUNK_BYTES = 32 << 20
+
+
+def upload(x, device, dtype: torch.dtype) -> torch.Tensor:
+    """Host array -> device tensor of ``dtype``.  A large pageable NumPy array goes through two page-locked 32 MB
+    staging buffers: torch's multi-threaded CPU copy (which also converts the dtype) fills one while the DMA engine
+    drains the other - 296 MB in 6.5 ms on the B200 host against 27 ms for the driver's own pageable path
+    (``tools/prof_h2d.py``).  The buffers are allocated once per dtype and kept."""
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype).contiguous()
+    src = torch.as_tensor(np.ascontiguousarray(x))
+    if src.numel() * src.element_size() < 2 * UPLOAD_CHUNK_BYTES:
+        return src.to(device=device, dtype=dtype, non_blocking=True)
+    key = (dtype, device.index)
+    if key not in _staging:
+        c = UPLOAD_CHUNK_BYTES // torch.empty(0, dtype=dtype).element_size()
+        try:
+            _staging[key] = ([torch.empty(c, dtype=dtype, pin_memory=True) for _ in range(2)],
+                             [torch.cuda.Event() for _ in range(2)])
+        except RuntimeError:  # page-locked memory exhausted
+            return src.to(device=device, dtype=dtype)
+    stage, events = _staging[key]
+    flat = src.reshape(-1)
+    n, c = flat.numel(), stage[0].numel()
+    with torch.cuda.device(device):
+        dst = torch.empty(n, dtype=dtype, device=device)
+        for i, o in enumerate(range(0, n, c)):
+            b = i & 1
+            events[b].synchronize()  # the DMA that last read this buffer is done (no-op for a fresh event)
+            m = min(c, n - o)
+            stage[b][:m].copy_(flat[o:o + m])
+            dst[o:o + m].copy_(stage[b][:m], non_blocking=True)
+            events[b].record()
+    return dst.view(src.shape)
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 

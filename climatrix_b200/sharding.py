@@ -158,14 +158,22 @@ def ok_on_devices(x_s, y_s, z, t_x, t_y, grid: bool, *, k: int, variogram_model:
 
 
 def _idw_two_bands(s_lat, s_lon, values, t_lat, t_lon, grid, *, k, power, k_min, dtype, dev, layout,
-                   min_bytes: int = 1 << 28):
-    """Large host-resident batch on a dense grid, one device: hide the device->host copy of the result.
+                   min_bytes: int = 1 << 28, stream_bands: int = 8):
+    """Large host-resident batch on a dense grid, one device: hide the copies behind the kernels (or the kernels
+    behind the copies).
 
-    The result of a big reconstruction (C5: 1.9 GB) takes tens of milliseconds to cross PCIe, and none of it can
-    start before the neighbour search has finished.  So the target rows are cut into a large first band and a
-    small second one: the first band's result streams into its columns of the page-locked output (one strided
-    DMA, ``cmx_copy_rows_to_host``) while the second band is still searching.  The upload of the values is
-    issued after the first search launch, so it overlaps too.  Returns None when the case does not apply.
+    The result of a big reconstruction (C5: 1.9 GB) takes tens of milliseconds to cross PCIe.
+
+    * Brute-force search (``set_search("brute")``): nothing can be copied before the search has finished, and the
+      search is long.  The target rows are cut into a large first band and a small second one: the first band's
+      result streams into its columns of the page-locked output (one strided DMA, ``cmx_copy_rows_to_host``) while
+      the second band is still searching; the upload of the values is issued after the first search launch.
+    * Cell-binned search (the default): the kernels are short and the copies are the job.  The values go up first
+      (``kernels.upload``: page-locked staging, 4x the pageable rate), then ``stream_bands`` equal row bands are
+      reconstructed one after the other and each band's download overlaps the next band's kernels - the call takes the
+      download of the result plus one band of compute.
+
+    Returns None when the case does not apply.
     """
     import torch
 
@@ -182,7 +190,7 @@ def _idw_two_bands(s_lat, s_lon, values, t_lat, t_lon, grid, *, k, power, k_min,
     m_total = n_rows * n_cols
     if n_batch < 2 or n_rows < 256 or m_total * n_batch * esize < min_bytes:
         return None
-    split = (int(0.92 * n_rows) // 16) * 16  # small second band: its search must still cover the first band's download
+    brute = kernels.get_search() == "brute"
     lib = _lib.load()
     with torch.cuda.device(dev):
         main = torch.cuda.current_stream(dev)
@@ -193,27 +201,43 @@ def _idw_two_bands(s_lat, s_lon, values, t_lat, t_lon, grid, *, k, power, k_min,
             return None
         s_lat_d, s_lon_d = kernels._as_f64(s_lat, dev), kernels._as_f64(s_lon, dev)
         t_lat_d, t_lon_d = kernels._as_f64(t_lat, dev), kernels._as_f64(t_lon, dev)
-        keep, vals_d, col = [], None, 0
-        for r0, r1 in ((0, split), (split, n_rows)):
-            tg = kernels.Targets(t_lat_d[r0:r1].contiguous(), t_lon_d, True)
-            dist, idx = kernels.knn(s_lat_d, s_lon_d, tg, k)  # asynchronous launch
-            if vals_d is None:  # pageable upload: the host stages it while the search kernel runs
-                with torch.cuda.stream(up):
-                    vals_d = torch.as_tensor(values).to(device=dev, dtype=dtype, non_blocking=True)
-                main.wait_stream(up)
-                vals_d.record_stream(main)
-            band = kernels.idw_apply(idx, dist, vals_d, k=k, power=power, k_min=k_min, dtype=dtype, layout=layout,
-                                     n_samples=n)
+        keep, col = [], 0
+
+        def download(band, r0, r1, stream):
+            nonlocal col
             m_band = (r1 - r0) * n_cols
-            stream = down if r1 < n_rows else main  # the last band has nothing left to overlap with
             if stream is down:
                 down.wait_stream(main)
                 band.record_stream(down)
             _lib.check(lib.cmx_copy_rows_to_host(host.data_ptr() + col * esize, m_total * esize, band.data_ptr(),
                                                  m_band * esize, m_band * esize, n_batch, stream.cuda_stream),
                        "cmx_copy_rows_to_host")
-            keep.append((band, dist, idx))
             col += m_band
+
+        if brute:
+            split = (int(0.92 * n_rows) // 16) * 16  # small second band: its search must still cover the first band's download
+            vals_d = None
+            for r0, r1 in ((0, split), (split, n_rows)):
+                tg = kernels.Targets(t_lat_d[r0:r1].contiguous(), t_lon_d, True)
+                dist, idx = kernels.knn(s_lat_d, s_lon_d, tg, k)  # asynchronous launch
+                if vals_d is None:  # staged by the host while the search kernel runs
+                    with torch.cuda.stream(up):
+                        vals_d = kernels.upload(values, dev, dtype)
+                    main.wait_stream(up)
+                    vals_d.record_stream(main)
+                band = kernels.idw_apply(idx, dist, vals_d, k=k, power=power, k_min=k_min, dtype=dtype, layout=layout,
+                                         n_samples=n)
+                download(band, r0, r1, down if r1 < n_rows else main)  # the last band has nothing left to overlap with
+                keep.append((band, dist, idx))
+        else:
+            vals_d = kernels.upload(values, dev, dtype)
+            for r0, r1 in row_shards(n_rows, stream_bands):
+                if r1 == r0:
+                    continue
+                tg = kernels.Targets(t_lat_d[r0:r1].contiguous(), t_lon_d, True)
+                band = kernels.idw(s_lat_d, s_lon_d, vals_d, tg, k=k, power=power, k_min=k_min, dtype=dtype, layout=layout)
+                download(band, r0, r1, down)
+                keep.append(band)
         down.synchronize()
         main.synchronize()
     return host.numpy()

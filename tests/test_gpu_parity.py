@@ -737,6 +737,21 @@ def test_idw_two_band_pipeline_equals_single_call(layout):
                           dev=torch.device(DEV), layout=layout) is None
 
 
+def test_staged_upload_is_exact_and_converts_dtype():
+    """kernels.upload: chunked copy through page-locked staging buffers (odd sizes, 2-D shape, dtype conversion,
+    repeated calls reuse the buffers) equals the plain copy."""
+    rng = np.random.default_rng(5)
+    big = rng.normal(size=(1_234_567, 9))                      # 89 MB: three chunks, the last one partial
+    dev = torch.device(DEV)
+    for _ in range(2):
+        for dt in (torch.float64, torch.float32):
+            got = K.upload(big, dev, dt)
+            assert got.shape == big.shape and got.dtype == dt and got.device.type == "cuda"
+            assert torch.equal(got.cpu(), torch.as_tensor(big).to(dt))
+    small = rng.normal(size=1000)
+    assert torch.equal(K.upload(small, dev, torch.float64).cpu(), torch.as_tensor(small))
+
+
 def test_ok_reconstructor_surfaces_the_kriging_variance():
     """pykrige's execute() returns (z, sigma^2); climatrix drops sigma^2 (kriging.py:236).  With
     return_variance=True the reconstructor keeps it, in data units^2."""
