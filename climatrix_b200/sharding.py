@@ -158,7 +158,7 @@ def ok_on_devices(x_s, y_s, z, t_x, t_y, grid: bool, *, k: int, variogram_model:
 
 
 def _idw_two_bands(s_lat, s_lon, values, t_lat, t_lon, grid, *, k, power, k_min, dtype, dev, layout,
-                   min_bytes: int = 1 << 28, stream_bands: int = 8):
+                   min_bytes: int = 1 << 26, stream_bands: int = 8):
     """Large host-resident batch on a dense grid, one device: hide the copies behind the kernels (or the kernels
     behind the copies).
 
@@ -188,7 +188,7 @@ def _idw_two_bands(s_lat, s_lon, values, t_lat, t_lon, grid, *, k, power, k_min,
     n_batch = values.shape[1] if layout == "sample_major" else values.shape[0]
     esize = 8 if dtype == torch.float64 else 4
     m_total = n_rows * n_cols
-    if n_batch < 2 or n_rows < 256 or m_total * n_batch * esize < min_bytes:
+    if n_batch < 2 or n_rows < 32 or m_total * n_batch * esize < min_bytes:
         return None
     brute = kernels.get_search() == "brute"
     lib = _lib.load()
@@ -215,9 +215,11 @@ def _idw_two_bands(s_lat, s_lon, values, t_lat, t_lon, grid, *, k, power, k_min,
             col += m_band
 
         if brute:
-            split = (int(0.92 * n_rows) // 16) * 16  # small second band: its search must still cover the first band's download
+            # small second band: its search must still cover the first band's download.  A band of a sharded job (a
+            # few hundred rows) is not cut again - its search still hides the upload of the values.
+            split = (int(0.92 * n_rows) // 16) * 16 if n_rows >= 512 else n_rows
             vals_d = None
-            for r0, r1 in ((0, split), (split, n_rows)):
+            for r0, r1 in ((0, split), (split, n_rows)) if split < n_rows else ((0, n_rows),):
                 tg = kernels.Targets(t_lat_d[r0:r1].contiguous(), t_lon_d, True)
                 dist, idx = kernels.knn(s_lat_d, s_lon_d, tg, k)  # asynchronous launch
                 if vals_d is None:  # staged by the host while the search kernel runs
@@ -231,7 +233,7 @@ def _idw_two_bands(s_lat, s_lon, values, t_lat, t_lon, grid, *, k, power, k_min,
                 keep.append((band, dist, idx))
         else:
             vals_d = kernels.upload(values, dev, dtype)
-            for r0, r1 in row_shards(n_rows, stream_bands):
+            for r0, r1 in row_shards(n_rows, max(1, min(stream_bands, n_rows // 32))):
                 if r1 == r0:
                     continue
                 tg = kernels.Targets(t_lat_d[r0:r1].contiguous(), t_lon_d, True)

@@ -726,12 +726,13 @@ def test_idw_two_band_pipeline_equals_single_call(layout):
     la, lo, _, rng = _samples(3000, 77)
     vals = rng.normal(size=(3000, 5))
     host_vals = vals if layout == "sample_major" else np.ascontiguousarray(vals.T)
-    tl, to = np.linspace(-80, 80, 300), np.linspace(-170, 170, 41)
-    got = _idw_two_bands(la, lo, host_vals, tl, to, True, k=12, power=2.0, k_min=2, dtype=torch.float64,
-                         dev=torch.device(DEV), layout=layout, min_bytes=0)
-    assert got is not None and got.shape == (5, 300 * 41)
-    ref = K.idw(la, lo, vals, K.Targets.make(tl, to, True, DEV), k=12, layout="sample_major").cpu().numpy()
-    np.testing.assert_array_equal(got, ref)
+    for n_rows in (300, 600, 45):   # one band with the upload overlapped / two bands (brute); 8 / 8 / 1 streamed bands (binned)
+        tl, to = np.linspace(-80, 80, n_rows), np.linspace(-170, 170, 41)
+        got = _idw_two_bands(la, lo, host_vals, tl, to, True, k=12, power=2.0, k_min=2, dtype=torch.float64,
+                             dev=torch.device(DEV), layout=layout, min_bytes=0)
+        assert got is not None and got.shape == (5, n_rows * 41)
+        ref = K.idw(la, lo, vals, K.Targets.make(tl, to, True, DEV), k=12, layout="sample_major").cpu().numpy()
+        np.testing.assert_array_equal(got, ref)
     # too small / not a batch: the pipeline declines and the plain path runs
     assert _idw_two_bands(la, lo, host_vals, tl, to, True, k=12, power=2.0, k_min=2, dtype=torch.float64,
                           dev=torch.device(DEV), layout=layout) is None
