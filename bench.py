@@ -673,6 +673,79 @@ class Runner:
         }
 
 
+def run_ok_global(runner, steps, warmup, with_e2e, with_cpu, n=5000, m=10000):
+    """The ordinary kriging climatrix SHIPS (no neighbour count: one (N+1)^2 system for all targets)
+    in the shape of the reference's own benchmark CSV (a few thousand stations -> 10 000 sparse
+    points).  Not sharded (every rank would solve the same system): part of the single-GPU line only."""
+    import climatrix_b200 as cm
+    from climatrix_b200.kriging import _anisotropy, _minmax_scale
+
+    torch, K, dev = runner.torch, runner.K, runner.dev
+    rng = np.random.default_rng(77)
+    lat, lon = rng.uniform(-90, 90, n), rng.uniform(-180, 180, n)
+    vals = 15.0 + 10.0 * np.cos(np.deg2rad(lat)) + 5.0 * np.sin(2.0 * np.deg2rad(lon)) + rng.normal(size=n)
+    t_lat, t_lon = rng.uniform(-90, 90, m), rng.uniform(-180, 180, m)
+    vals_d = torch.as_tensor(vals).to(dev)
+    state = {}
+
+    def step():  # the whole reference call with resident inputs: normalise, variogram + fit, one solve, M predictions
+        lat_n, lon_n = _minmax_scale(lat), _minmax_scale(lon)
+        mean, std = float(np.nanmean(vals)), float(np.nanstd(vals))
+        z = (vals_d - mean) / std
+        xs, ys = torch.as_tensor(lon_n).to(dev), torch.as_tensor(lat_n).to(dev)
+        lags, sv, _ = K.empirical_variogram(xs, ys, z, 6)
+        params = K.fit_variogram_native(lags, sv, "spherical")
+        out, status = K.ok_global(xs, ys, z, _minmax_scale(t_lon), _minmax_scale(t_lat), False, variogram_model="spherical",
+                                  params=params, out_scale=std, out_shift=mean)
+        state["params"], state["status"] = params, status
+        return out
+
+    run = runner.timed(step, steps, warmup, "auto")
+    ms = run["ms_per_step"]
+    field = run["last"].cpu().numpy()
+    coords = {"point": np.arange(n), "latitude": (("point",), lat), "longitude": (("point",), lon)}
+    src = cm.BaseClimatrixDataset(cm.FieldArray(vals, ("point",), coords, name="field"))
+    tgt = cm.Domain.from_lat_lon(t_lat, t_lon, kind="sparse")
+    kw = dict(variogram_model="spherical", nlags=6, anisotropy_scaling=1.0)
+    e2e = None
+    if with_e2e:
+        for _ in range(2):
+            src.reconstruct(tgt, method="ok", **kw)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            got = src.reconstruct(tgt, method="ok", **kw)
+        sec = (time.perf_counter() - t0) / 3
+        e2e = {"value": m / sec, "unit": "targets/s", "h2d_bytes_per_step": int((3 * n + 2 * m) * 8), "d2h_bytes_per_step": int(m * 8),
+               "ms_per_step": sec * 1e3, "steps": 3,
+               "api": "BaseClimatrixDataset.reconstruct(sparse_domain, method='ok', ...) without n_closest_points, NumPy in and out"}
+    cpu = parity = None
+    if with_cpu:  # the restated reference call in full (it is small enough): also the parity check
+        from oracle.ok_oracle import ok_oracle
+
+        t0 = time.perf_counter()
+        want = ok_oracle(lat, lon, vals, t_lat, t_lon, True, nlags=6, anisotropy_scaling=1.0, variogram_model="spherical")
+        sec = time.perf_counter() - t0
+        err = float(np.max(np.abs(field - want)) / np.max(np.abs(want)))
+        parity = {"parity_checked": True, "max_rel_err": err, "tolerance": 1e-4, "ok": bool(err <= 1e-4),
+                  "what": f"all {m} targets vs oracle/pykrige_restated.py (variogram, fit, inv(A), vectorized execute)"}
+        cpu = {"value": m / sec, "unit": "targets/s", "cores": runner.cores, "kind": "port",
+               "sample": f"the whole restated call, {sec:.1f} s: pdist variogram + least_squares + scipy.linalg.inv of the "
+                         f"{n + 1}^2 matrix + A^-1 b for {m} targets (BLAS threads = host cores)"}
+    flops = 2.0 * n ** 3 / 3.0 + 30.0 * n * (n - 1) / 2 + 25.0 * n * m  # factorisation + assembly + predictions
+    return {"value": m / (ms * 1e-3), "unit": "targets/s", "ms_per_step": ms, "e2e": e2e, "gpu_launches": int(run["launches"]),
+            "roofline": {"kernel": "gk_* (K5: blocked Cholesky of the shifted (N+1)^2 system + predictions)", "bound": "fp64",
+                         "achieved": flops / (ms * 1e-3) / 1e12, "peak": K.fp64_peak_tflops(), "unit": "TFLOP/s",
+                         "frac": flops / (ms * 1e-3) / 1e12 / K.fp64_peak_tflops(), "algorithmic_flops_per_launch": flops,
+                         "note": "whole step / algorithmic flops (the step is ~all K5); traffic not captured", "traffic": None},
+            "cpu_baseline": cpu, "parity_checked": bool(parity), "max_rel_err": parity["max_rel_err"] if parity else None,
+            "parity": parity, "variogram_parameters": [float(v) for v in state["params"]], "solver_status": int(state["status"]),
+            "config": {"workload": f"g: OK global (the mode climatrix ships), {n} samples -> {m} sparse points, spherical variogram",
+                       "samples": n, "targets": m, "method": "ok", "k": None, "sharding": "none (one system)"},
+            "vs_baseline": None,
+            "notes": "BASELINE.md section 1 quotes 139.5 s for 10 000 points with pykrige on unrecorded hardware and data; "
+                     "different inputs, so no vs_baseline"}
+
+
 def reference_arm(args):
     """``--impl reference``: the reference's CPU path on the host cores, rank 0 only, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -747,6 +820,8 @@ def main():
                 sub = runner.run_ok(name, max(1, min(args.steps, 5)), max(3, min(args.warmup, 3)), "auto", not args.no_e2e, with_cpu)
                 ok[name] = {key: sub[key] for key in ("value", "unit", "ms_per_step", "e2e", "gpu_launches", "roofline", "cpu_baseline",
                                                       "config", "variogram_parameters", "parity_checked", "max_rel_err", "parity", "notes")}
+            if runner.world == 1:  # one system, nothing to shard: reported by the single-GPU run only
+                ok["global"] = run_ok_global(runner, max(1, min(args.steps, 5)), 3, not args.no_e2e, with_cpu)
             line["ok"] = ok
     else:
         line = runner.run_ok(args.workload, args.steps, args.warmup, "auto" if args.search == "brute" else args.search,

@@ -100,40 +100,72 @@ __global__ void gk_copy_kernel(double* __restrict__ dst, const double* __restric
 }
 
 // ---- blocked Cholesky ----------------------------------------------------------------------------------------------
-// diagonal block kb: unblocked Cholesky of a (up to) 64 x 64 block in shared memory.  *fail |= 1 on a pivot <= thr.
+// diagonal block kb: unblocked Cholesky of a (up to) 64 x 64 block.  *fail |= 1 on a pivot <= thr.
+// 16 x 16 threads, each keeps a 4 x 4 sub-tile (rows ty + 16 a, columns tx + 16 b) in registers; per column the owners
+// publish the raw column to a double-buffered shared vector, ONE barrier, everybody scales it by the reciprocal root of
+// its head and updates its own registers.
 __global__ void __launch_bounds__(256) gk_potrf_kernel(double* __restrict__ C, long long ld, long long n, int kb,
                                                        const double* gmax, int* fail) {
-    __shared__ double s[GB][GB + 1];
+    __shared__ double col[2][GB];
     const long long r0 = (long long)kb * GB;
     const int nb = (int)(n - r0 < GB ? n - r0 : GB);
-    const int tid = threadIdx.x;
-    for (int e = tid; e < GB * GB; e += 256) {
-        const int i = e / GB, j = e % GB;
-        s[i][j] = (i < nb && j <= i) ? C[(r0 + i) * ld + r0 + j] : (i == j ? 1.0 : 0.0);
-    }
-    __syncthreads();
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    double t[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int i = ty + 16 * a, m = tx + 16 * b;
+            t[a][b] = (i < nb && m <= i) ? C[(r0 + i) * ld + r0 + m] : (i == m ? 1.0 : 0.0);
+        }
     const double thr = 1.0e-13 * 2.0 * *gmax;
-    for (int j = 0; j < nb; ++j) {
-        double d = s[j][j];
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < GB; ++j) {
+        const int bj = j >> 4, xj = j & 15;  // column j lives in sub-tile column bj of the threads with tx == xj
+        if (tx == xj) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) col[j & 1][ty + 16 * a] = t[a][bj];
+        }
+        __syncthreads();
+        double d = col[j & 1][j];
         if (!(d > thr)) {
-            if (tid == 0) atomicOr(fail, 1);
+            bad = true;
             d = thr > 0.0 ? thr : 1.0;
         }
         const double rinv = 1.0 / sqrt(d);
-        __syncthreads();
-        if (tid == 0) s[j][j] = sqrt(d);
-        for (int i = j + 1 + tid; i < nb; i += 256) s[i][j] *= rinv;
-        __syncthreads();
-        for (int e = tid; e < (nb - j - 1) * (nb - j - 1); e += 256) {
-            const int i = j + 1 + e / (nb - j - 1), m = j + 1 + e % (nb - j - 1);
-            if (m <= i) s[i][m] -= s[i][j] * s[m][j];
+        double ci[4], cm[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int i = ty + 16 * a;
+            ci[a] = i > j ? col[j & 1][i] * rinv : 0.0;
         }
-        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int m = tx + 16 * b;
+            cm[b] = m > j ? col[j & 1][m] * rinv : 0.0;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) t[a][b] = fma(-ci[a], cm[b], t[a][b]);  // (entries above the diagonal are never stored)
+        if (tx == xj) {  // the finished column: L[j][j] = sqrt(d), L[i][j] = c_i / sqrt(d)
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int i = ty + 16 * a;
+                if (i == j) t[a][bj] = sqrt(d);
+                else if (i > j) t[a][bj] = ci[a];
+            }
+        }
     }
-    for (int e = tid; e < GB * GB; e += 256) {
-        const int i = e / GB, j = e % GB;
-        if (i < nb && j <= i) C[(r0 + i) * ld + r0 + j] = s[i][j];
-    }
+    if (bad && tid == 0) atomicOr(fail, 1);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int i = ty + 16 * a, m = tx + 16 * b;
+            if (i < nb && m <= i) C[(r0 + i) * ld + r0 + m] = t[a][b];
+        }
 }
 // panel below the diagonal block: X L_kk' = C_ik, one thread per row
 __global__ void __launch_bounds__(GB) gk_trsm_kernel(double* __restrict__ C, long long ld, long long n, int kb) {
@@ -151,12 +183,11 @@ __global__ void __launch_bounds__(GB) gk_trsm_kernel(double* __restrict__ C, lon
 #pragma unroll
     for (int j = 0; j < GB; ++j) x[j] = c[j];
 #pragma unroll
-    for (int j = 0; j < GB; ++j) {
-        double a = x[j];
+    for (int j = 0; j < GB; ++j) {  // column-oriented: the updates of one step are independent of each other
+        x[j] = x[j] / L[j][j];
 #pragma unroll
         for (int m = 0; m < GB; ++m)
-            if (m < j) a = fma(-x[m], L[j][m], a);
-        x[j] = a / L[j][j];
+            if (m > j) x[m] = fma(-x[j], L[m][j], x[m]);
     }
 #pragma unroll
     for (int j = 0; j < GB; ++j) c[j] = x[j];
@@ -211,95 +242,102 @@ __global__ void __launch_bounds__(256) gk_syrk_kernel(double* __restrict__ C, lo
     }
 }
 
-// ---- triangular solves with two right-hand sides (one persistent CTA; O(N^2) work in total) ---------------------
-// rhs [2][n]: rhs 0 = Z, rhs 1 = ones; overwritten by L^-1 rhs
-__global__ void __launch_bounds__(256) gk_forward_kernel(const double* __restrict__ C, long long ld, long long n,
-                                                         double* __restrict__ rhs) {
-    __shared__ double L[GB][GB + 1];
-    __shared__ double xs[2][GB];
-    const int tid = threadIdx.x;
-    const long long nblk = (n + GB - 1) / GB;
-    for (long long kb = 0; kb < nblk; ++kb) {
-        const long long r0 = kb * GB;
-        const int nb = (int)(n - r0 < GB ? n - r0 : GB);
-        for (int e = tid; e < GB * GB; e += 256) {
-            const int i = e / GB, j = e % GB;
-            L[i][j] = (i < nb && j <= i) ? C[(r0 + i) * ld + r0 + j] : (i == j ? 1.0 : 0.0);
-        }
-        if (tid < 2 * GB) xs[tid / GB][tid % GB] = (tid % GB) < nb ? rhs[(tid / GB) * n + r0 + tid % GB] : 0.0;
-        __syncthreads();
-        for (int c = 0; c < nb; ++c) {  // column-oriented forward substitution on the diagonal block
-            if (tid < 2) xs[tid][c] /= L[c][c];
-            __syncthreads();
-            if (tid < 2 * GB) {
-                const int q = tid / GB, i = tid % GB;
-                if (i > c && i < nb) xs[q][i] -= L[i][c] * xs[q][c];
-            }
-            __syncthreads();
-        }
-        if (tid < 2 * GB && (tid % GB) < nb) rhs[(tid / GB) * n + r0 + tid % GB] = xs[tid / GB][tid % GB];
-        // the rows below: rhs_i -= L[i][block] . x
-        for (long long i = r0 + GB + tid; i < n; i += 256) {
-            const double* row = C + i * ld + r0;
-            double a0 = 0.0, a1 = 0.0;
-#pragma unroll 8
-            for (int c = 0; c < GB; ++c) {
-                const double l = row[c];
-                a0 = fma(l, xs[0][c], a0);
-                a1 = fma(l, xs[1][c], a1);
-            }
-            rhs[i] -= a0;
-            rhs[n + i] -= a1;
-        }
-        __syncthreads();
+// ---- triangular solves with two right-hand sides, one launch per block step ------------------------------------------
+// Every CTA of a step solves the 64 x 64 diagonal block ITSELF (one warp per right-hand side: 64 serial steps over warp
+// shuffles, ~2 us - cheaper than a round trip through global memory and a grid-wide wait), CTA 0 stores the block of the
+// solution, every other CTA subtracts its 64 x 64 tile times that block from its part of the working vector.
+__device__ __forceinline__ void gk_load_diag(const double* __restrict__ C, long long ld, long long r0, int nb,
+                                             double (*L)[GB + 1]) {
+    for (int e = threadIdx.x; e < GB * GB; e += blockDim.x) {
+        const int i = e / GB, j = e % GB;
+        L[i][j] = (i < nb && j <= i) ? C[(r0 + i) * ld + r0 + j] : (i == j ? 1.0 : 0.0);
     }
 }
-// rhs [2][n] overwritten by L^-T rhs
-__global__ void __launch_bounds__(256) gk_backward_kernel(const double* __restrict__ C, long long ld, long long n,
-                                                          double* __restrict__ rhs) {
+// L y = b.  work [2][n]: b on entry, rows below block kb updated; y [2][n]: block kb of the solution.  Grid: 1 + blocks below.
+__global__ void __launch_bounds__(128) gk_forward_step_kernel(const double* __restrict__ C, long long ld, long long n, int kb,
+                                                              double* __restrict__ work, double* __restrict__ y) {
     __shared__ double L[GB][GB + 1];
     __shared__ double xs[2][GB];
-    __shared__ double part[4][2][GB];
-    const int tid = threadIdx.x;
-    const long long nblk = (n + GB - 1) / GB;
-    for (long long kb = nblk - 1; kb >= 0; --kb) {
-        const long long r0 = kb * GB;
-        const int nb = (int)(n - r0 < GB ? n - r0 : GB);
-        // s_c = sum over the rows below of L[i][r0 + c] * x_i (x already final there): 64 columns x 4 row groups
-        {
-            const int c = tid % GB, rg = tid / GB;
-            double a0 = 0.0, a1 = 0.0;
-            for (long long i = r0 + GB + rg; i < n; i += 4) {
-                const double l = C[i * ld + r0 + c];
-                a0 = fma(l, rhs[i], a0);
-                a1 = fma(l, rhs[n + i], a1);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long r0 = (long long)kb * GB;
+    const int nb = (int)(n - r0 < GB ? n - r0 : GB);
+    gk_load_diag(C, ld, r0, nb, L);
+    __syncthreads();
+    if (warp < 2) {
+        double x0 = lane < nb ? work[warp * n + r0 + lane] : 0.0;
+        double x1 = lane + 32 < nb ? work[warp * n + r0 + lane + 32] : 0.0;
+        for (int c = 0; c < GB; ++c) {
+            const double xc = __shfl_sync(kFull, c < 32 ? x0 : x1, c & 31) / L[c][c];
+            if (lane == (c & 31)) {
+                if (c < 32) x0 = xc;
+                else x1 = xc;
             }
-            part[rg][0][c] = a0;
-            part[rg][1][c] = a1;
+            if (lane > c) x0 = fma(-L[lane][c], xc, x0);
+            if (lane + 32 > c) x1 = fma(-L[lane + 32][c], xc, x1);
         }
-        for (int e = tid; e < GB * GB; e += 256) {
-            const int i = e / GB, j = e % GB;
-            L[i][j] = (i < nb && j <= i) ? C[(r0 + i) * ld + r0 + j] : (i == j ? 1.0 : 0.0);
-        }
-        __syncthreads();
-        if (tid < 2 * GB) {
-            const int q = tid / GB, c = tid % GB;
-            const double s = (part[0][q][c] + part[1][q][c]) + (part[2][q][c] + part[3][q][c]);
-            xs[q][c] = c < nb ? rhs[q * n + r0 + c] - s : 0.0;
-        }
-        __syncthreads();
-        for (int c = nb - 1; c >= 0; --c) {  // L' x = y: back substitution, row c of L' is column c of L
-            if (tid < 2) xs[tid][c] /= L[c][c];
-            __syncthreads();
-            if (tid < 2 * GB) {
-                const int q = tid / GB, i = tid % GB;
-                if (i < c) xs[q][i] -= L[c][i] * xs[q][c];
-            }
-            __syncthreads();
-        }
-        if (tid < 2 * GB && (tid % GB) < nb) rhs[(tid / GB) * n + r0 + tid % GB] = xs[tid / GB][tid % GB];
-        __syncthreads();
+        xs[warp][lane] = x0;
+        xs[warp][lane + 32] = x1;
     }
+    __syncthreads();
+    const int q = tid >> 6, i = tid & 63;
+    if (blockIdx.x == 0) {
+        if (i < nb) y[q * n + r0 + i] = xs[q][i];
+        return;
+    }
+    const long long rb = r0 + (long long)blockIdx.x * GB;  // my rows
+    for (int e = tid; e < GB * GB; e += 128) {
+        const int r = e / GB, c = e % GB;
+        L[r][c] = rb + r < n ? C[(rb + r) * ld + r0 + c] : 0.0;
+    }
+    __syncthreads();
+    if (rb + i < n) {
+        double a = 0.0;
+#pragma unroll 8
+        for (int c = 0; c < GB; ++c) a = fma(L[i][c], xs[q][c], a);
+        work[q * n + rb + i] -= a;
+    }
+}
+// L' x = y.  work [2][n]: y on entry, blocks left of kb updated; x [2][n]: block kb of the solution.  Grid: 1 + kb.
+__global__ void __launch_bounds__(128) gk_backward_step_kernel(const double* __restrict__ C, long long ld, long long n, int kb,
+                                                               double* __restrict__ work, double* __restrict__ x) {
+    __shared__ double L[GB][GB + 1];
+    __shared__ double xs[2][GB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long r0 = (long long)kb * GB;
+    const int nb = (int)(n - r0 < GB ? n - r0 : GB);
+    gk_load_diag(C, ld, r0, nb, L);
+    __syncthreads();
+    if (warp < 2) {
+        double x0 = lane < nb ? work[warp * n + r0 + lane] : 0.0;
+        double x1 = lane + 32 < nb ? work[warp * n + r0 + lane + 32] : 0.0;
+        for (int c = GB - 1; c >= 0; --c) {  // row c of L' is column c of L
+            const double xc = __shfl_sync(kFull, c < 32 ? x0 : x1, c & 31) / L[c][c];
+            if (lane == (c & 31)) {
+                if (c < 32) x0 = xc;
+                else x1 = xc;
+            }
+            if (lane < c) x0 = fma(-L[c][lane], xc, x0);
+            if (lane + 32 < c) x1 = fma(-L[c][lane + 32], xc, x1);
+        }
+        xs[warp][lane] = x0;
+        xs[warp][lane + 32] = x1;
+    }
+    __syncthreads();
+    const int q = tid >> 6, i = tid & 63;
+    if (blockIdx.x == 0) {
+        if (i < nb) x[q * n + r0 + i] = xs[q][i];
+        return;
+    }
+    const long long cb = (long long)(blockIdx.x - 1) * GB;  // my columns: a block left of the diagonal
+    for (int e = tid; e < GB * GB; e += 128) {
+        const int r = e / GB, c = e % GB;
+        L[r][c] = r < nb ? C[(r0 + r) * ld + cb + c] : 0.0;
+    }
+    __syncthreads();
+    double a = 0.0;
+#pragma unroll 8
+    for (int r = 0; r < GB; ++r) a = fma(L[r][i], xs[q][r], a);
+    work[q * n + cb + i] -= a;
 }
 // lambda = 1'y / 1'u, w = y - lambda u  (single CTA; w_ext[n] = lambda)
 __global__ void __launch_bounds__(256) gk_combine_kernel(long long n, const double* __restrict__ yu, double* __restrict__ w_ext) {
@@ -557,10 +595,19 @@ int gk_entry(const double* s_x, const double* s_y, const double* z, long long n,
             CMX_CUDA(cudaMemcpyAsync(rhs, z, (size_t)n * 8, cudaMemcpyDeviceToDevice, stream));
             gk_fill_kernel<<<64, 256, 0, stream>>>(rhs + n, 1.0, n);
             note_launch();
-            gk_forward_kernel<<<1, 256, 0, stream>>>(C, n, n, rhs);
-            gk_backward_kernel<<<1, 256, 0, stream>>>(C, n, n, rhs);
+            // forward: rhs -> y (the two slots the Jacobi path uses for sigma2 | dots); backward: y -> rhs
+            double* ysol = sigma2;
+            static_assert(sizeof(double) == 8, "");
+            for (long long kb = 0; kb < nblk; ++kb) {
+                gk_forward_step_kernel<<<(unsigned)(nblk - kb), 128, 0, stream>>>(C, n, n, (int)kb, rhs, ysol);
+                note_launch();
+            }
+            for (long long kb = nblk - 1; kb >= 0; --kb) {
+                gk_backward_step_kernel<<<(unsigned)(kb + 1), 128, 0, stream>>>(C, n, n, (int)kb, ysol, rhs);
+                note_launch();
+            }
             gk_combine_kernel<<<1, 256, 0, stream>>>(n, rhs, w_ext);
-            for (int i = 0; i < 3; ++i) note_launch();
+            note_launch();
         }
     }
     if (jacobi) {
