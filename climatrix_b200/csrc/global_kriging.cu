@@ -46,6 +46,16 @@ __device__ __forceinline__ double gk_distance(int metric, double xi, double yi, 
     return sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
 }
 
+// 1 / sqrt(d) for a positive normal d: hardware seed + two Newton steps (1-2 ulp), no slow-path branch
+__device__ __forceinline__ double gk_rsqrt(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double h = 0.5 * d;
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    return y;
+}
+
 struct GkParams {
     int model, metric;
     double p0, p1, p2;
@@ -133,7 +143,7 @@ __global__ void __launch_bounds__(256) gk_potrf_kernel(double* __restrict__ C, l
             bad = true;
             d = thr > 0.0 ? thr : 1.0;
         }
-        const double rinv = 1.0 / sqrt(d);
+        const double rinv = gk_rsqrt(d);
         double ci[4], cm[4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
@@ -153,7 +163,7 @@ __global__ void __launch_bounds__(256) gk_potrf_kernel(double* __restrict__ C, l
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
                 const int i = ty + 16 * a;
-                if (i == j) t[a][bj] = sqrt(d);
+                if (i == j) t[a][bj] = d * rinv;
                 else if (i > j) t[a][bj] = ci[a];
             }
         }
@@ -170,11 +180,14 @@ __global__ void __launch_bounds__(256) gk_potrf_kernel(double* __restrict__ C, l
 // panel below the diagonal block: X L_kk' = C_ik, one thread per row
 __global__ void __launch_bounds__(GB) gk_trsm_kernel(double* __restrict__ C, long long ld, long long n, int kb) {
     __shared__ double L[GB][GB + 1];
+    __shared__ double dinv[GB];
     const long long r0 = (long long)kb * GB;
     for (int e = threadIdx.x; e < GB * GB; e += GB) {
         const int i = e / GB, j = e % GB;
         L[i][j] = j <= i ? C[(r0 + i) * ld + r0 + j] : 0.0;
     }
+    __syncthreads();
+    dinv[threadIdx.x] = 1.0 / L[threadIdx.x][threadIdx.x];
     __syncthreads();
     const long long row = r0 + GB + (long long)blockIdx.x * GB + threadIdx.x;
     if (row >= n) return;
@@ -184,7 +197,7 @@ __global__ void __launch_bounds__(GB) gk_trsm_kernel(double* __restrict__ C, lon
     for (int j = 0; j < GB; ++j) x[j] = c[j];
 #pragma unroll
     for (int j = 0; j < GB; ++j) {  // column-oriented: the updates of one step are independent of each other
-        x[j] = x[j] / L[j][j];
+        x[j] = x[j] * dinv[j];
 #pragma unroll
         for (int m = 0; m < GB; ++m)
             if (m > j) x[m] = fma(-x[j], L[m][j], x[m]);
@@ -258,16 +271,20 @@ __global__ void __launch_bounds__(128) gk_forward_step_kernel(const double* __re
                                                               double* __restrict__ work, double* __restrict__ y) {
     __shared__ double L[GB][GB + 1];
     __shared__ double xs[2][GB];
+    __shared__ double dinv[GB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long r0 = (long long)kb * GB;
     const int nb = (int)(n - r0 < GB ? n - r0 : GB);
     gk_load_diag(C, ld, r0, nb, L);
     __syncthreads();
+    if (tid < GB) dinv[tid] = 1.0 / L[tid][tid];
+    __syncthreads();
     if (warp < 2) {
         double x0 = lane < nb ? work[warp * n + r0 + lane] : 0.0;
         double x1 = lane + 32 < nb ? work[warp * n + r0 + lane + 32] : 0.0;
+#pragma unroll 8
         for (int c = 0; c < GB; ++c) {
-            const double xc = __shfl_sync(kFull, c < 32 ? x0 : x1, c & 31) / L[c][c];
+            const double xc = __shfl_sync(kFull, c < 32 ? x0 : x1, c & 31) * dinv[c];
             if (lane == (c & 31)) {
                 if (c < 32) x0 = xc;
                 else x1 = xc;
@@ -302,16 +319,20 @@ __global__ void __launch_bounds__(128) gk_backward_step_kernel(const double* __r
                                                                double* __restrict__ work, double* __restrict__ x) {
     __shared__ double L[GB][GB + 1];
     __shared__ double xs[2][GB];
+    __shared__ double dinv[GB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long r0 = (long long)kb * GB;
     const int nb = (int)(n - r0 < GB ? n - r0 : GB);
     gk_load_diag(C, ld, r0, nb, L);
     __syncthreads();
+    if (tid < GB) dinv[tid] = 1.0 / L[tid][tid];
+    __syncthreads();
     if (warp < 2) {
         double x0 = lane < nb ? work[warp * n + r0 + lane] : 0.0;
         double x1 = lane + 32 < nb ? work[warp * n + r0 + lane + 32] : 0.0;
+#pragma unroll 8
         for (int c = GB - 1; c >= 0; --c) {  // row c of L' is column c of L
-            const double xc = __shfl_sync(kFull, c < 32 ? x0 : x1, c & 31) / L[c][c];
+            const double xc = __shfl_sync(kFull, c < 32 ? x0 : x1, c & 31) * dinv[c];
             if (lane == (c & 31)) {
                 if (c < 32) x0 = xc;
                 else x1 = xc;
