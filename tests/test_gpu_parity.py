@@ -88,6 +88,34 @@ def test_knn_clustered_samples_small_distances():
     np.testing.assert_array_equal(dist.cpu().numpy(), d0)
 
 
+def test_knn_chained_bound_on_point_sequences_with_small_steps():
+    """The binned search seeds a target's k-th-distance bound from the previous target of the warp (triangle
+    inequality) when the step is short.  Sparse target lists that walk in small steps through regions of very
+    different sample density, with repeated points and jumps, must still reproduce cKDTree bit for bit (the brute-force
+    run of this test checks the same inputs against the other kernel)."""
+    rng = np.random.default_rng(2024)
+    # a dense cluster inside a sparse background: d_k changes by two orders of magnitude along the walk
+    la = np.concatenate([rng.uniform(-60, 60, 6000), 10 + rng.normal(scale=0.3, size=6000)])
+    lo = np.concatenate([rng.uniform(-120, 120, 6000), 20 + rng.normal(scale=0.3, size=6000)])
+    steps = rng.normal(scale=0.02, size=(20000, 2))
+    steps[rng.random(20000) < 0.05] = 0.0                       # repeated target points
+    jumps = rng.random(20000) < 0.002
+    steps[jumps] = rng.normal(scale=15.0, size=(int(jumps.sum()), 2))
+    walk = np.array([8.0, 17.0]) + np.cumsum(steps, axis=0)
+    tl, to = np.clip(walk[:, 0], -89, 89), np.clip(walk[:, 1], -179, 179)
+    for k in (1, 7, 32, 64):
+        dist, idx = K.knn(la, lo, K.Targets.make(tl, to, False, DEV), k)
+        d0, i0 = knn_ckdtree(sparse_points(la, lo), sparse_points(tl, to), k)
+        np.testing.assert_array_equal(idx.cpu().numpy(), i0.reshape(len(tl), k))
+        np.testing.assert_array_equal(dist.cpu().numpy(), d0.reshape(len(tl), k))
+    # a fine grid over the edge of the cluster (steps of 0.01 deg, rows wrap around)
+    gl, go = np.linspace(8.5, 11.5, 150), np.linspace(18.5, 21.5, 301)
+    dist, idx = K.knn(la, lo, K.Targets.make(gl, go, True, DEV), 32)
+    d0, i0 = knn_ckdtree(sparse_points(la, lo), dense_points(gl, go), 32)
+    np.testing.assert_array_equal(idx.cpu().numpy(), i0)
+    np.testing.assert_array_equal(dist.cpu().numpy(), d0)
+
+
 def test_knn_far_away_targets_and_two_scales():
     """Targets well outside the sample bounding box, and a mix of a dense cluster and a sparse halo."""
     rng = np.random.default_rng(13)
