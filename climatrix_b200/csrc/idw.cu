@@ -482,17 +482,15 @@ __global__ void __launch_bounds__(256) idw_apply_single_kernel(const int* __rest
                                                                 const V* __restrict__ truth, double* __restrict__ part) {
     const int lane = threadIdx.x & 31;
     const long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (m >= M) {
-        if (SCORE) score_cta_partial(0.0, 0.0, 0.0, part);
-        return;
-    }
+    const bool live = m < M;  // (warp-uniform; with SCORE every warp reaches the CTA-wide reduction below)
+    if (!live && !SCORE) return;
     double w[CMX_MAX_K / 32];
     double wsum = 0.0;
 #pragma unroll
     for (int e = 0; e < CMX_MAX_K / 32; ++e) {
         const int j = e * 32 + lane;
         w[e] = 0.0;
-        if (j < k_use) {
+        if (live && j < k_use) {
             const double d = dd[m * k_table + j];
             const int id = idx[m * k_table + j];
             if (id >= 0 && id < n_samples) w[e] = dist_is_squared ? idw_raw_weight(d, power) : idw_weight_from_dist(d, power);
@@ -520,10 +518,10 @@ __global__ void __launch_bounds__(256) idw_apply_single_kernel(const int* __rest
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) fin += __shfl_xor_sync(kFull, fin, o);
     const V r = (fin < k_min || den == 0.0) ? quiet_nan<V>() : (V)(num / den);
-    if (lane == 0 && out) out[m] = r;
+    if (live && lane == 0 && out) out[m] = r;
     if (SCORE) {
         double ad = 0.0, sq = 0.0, cnt = 0.0;
-        if (lane == 0) {
+        if (live && lane == 0) {
             const double d = (double)r - (double)truth[m];  // the field as stored (rounded to V), like the reference
             if (isfinite(d)) {
                 ad = fabs(d);
