@@ -781,6 +781,30 @@ def test_staged_upload_is_exact_and_converts_dtype():
     assert torch.equal(K.upload(small, dev, torch.float64).cpu(), torch.as_tensor(small))
 
 
+def test_integration_md_ctypes_stub_runs_as_written():
+    """The ctypes binding shown in INTEGRATION.md section 4 is executed verbatim (only the library path is made
+    absolute) and must give the field of the package's own host layer."""
+    import os
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    stub = next(b for b in blocks if "def idw_gpu" in b)
+    stub = stub.replace('"climatrix_b200/lib/libclimatrix_b200.so"', repr(os.path.join(root, "climatrix_b200", "lib", "libclimatrix_b200.so")))
+    ns = {}
+    exec(compile(stub, "INTEGRATION.md", "exec"), ns)
+    la, lo, v, _ = _samples(5000, 314)
+    tl, to = np.linspace(-70, 70, 57), np.linspace(-160, 160, 131)
+    dev = torch.device(DEV)
+    args = [torch.as_tensor(a).to(dev) for a in (la, lo, v, tl, to)]
+    got = ns["idw_gpu"](*args, k=9, k_min=2, power=2.0)
+    torch.cuda.synchronize()
+    want = K.idw(la, lo, v, K.Targets.make(tl, to, True, DEV), k=9, k_min=2, power=2.0)
+    assert got.shape == (57, 131)
+    assert torch.equal(got.reshape(-1), want.reshape(-1))
+
+
 def test_ok_reconstructor_surfaces_the_kriging_variance():
     """pykrige's execute() returns (z, sigma^2); climatrix drops sigma^2 (kriging.py:236).  With
     return_variance=True the reconstructor keeps it, in data units^2."""
