@@ -23,7 +23,7 @@ class Options(ctypes.Structure):
     """``cmx_options`` of include/climatrix_b200.h: everything optional about a call, passed explicitly."""
 
     _fields_ = [("search", c_int), ("n_peers", c_int), ("peer_out", c_void_p * MAX_PEERS), ("m_total", c_i64),
-                ("m_offset", c_i64), ("params_on_device", c_int), ("peer_multicast", c_int)]
+                ("m_offset", c_i64), ("params_on_device", c_int)]
 
 
 SEARCH_AUTO, SEARCH_BRUTE, SEARCH_BINNED = 0, 1, 2

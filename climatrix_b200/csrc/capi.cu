@@ -14,7 +14,7 @@ void note_launch() { ++g_launches; }
 
 int read_options(const cmx_options* opt, int* search, PeerOut* peers, int* params_on_device) {
     if (search) *search = CMX_SEARCH_AUTO;
-    if (peers) peers->n = 0, peers->multicast = 0;
+    if (peers) peers->n = 0;
     if (params_on_device) *params_on_device = 0;
     if (!opt) return CMX_OK;
     if (opt->params_on_device && !params_on_device) return CMX_ERR_UNSUPPORTED;
@@ -31,8 +31,6 @@ int read_options(const cmx_options* opt, int* search, PeerOut* peers, int* param
         if (!opt->peer_out[i]) return CMX_ERR_BAD_ARG;
         peers->base[i] = opt->peer_out[i];
     }
-    if (opt->peer_multicast && opt->n_peers != 1) return CMX_ERR_BAD_ARG;
-    peers->multicast = opt->peer_multicast != 0;
     peers->n = opt->n_peers;
     peers->m_total = opt->m_total;
     peers->m_off = opt->m_offset;
@@ -112,7 +110,7 @@ int sm_count() {
 
 extern "C" {
 
-int cmx_version(void) { return 201; }  // 0.2.x: explicit cmx_options, no per-thread mode; .1: peer_multicast
+int cmx_version(void) { return 200; }  // 0.2.0: explicit cmx_options, no per-thread mode
 
 const char* cmx_strerror(int code) {
     switch (code) {

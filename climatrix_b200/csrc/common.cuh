@@ -22,7 +22,6 @@ struct PeerOut {
     void* base[CMX_MAX_PEERS];
     int n;  // 0: plain output
     long long m_total, m_off;
-    int multicast;  // base[0] is a multicast (NVLS) address: store with multimem.st
 };
 // validated copy of the caller's options (NULL -> defaults); returns CMX_OK or CMX_ERR_BAD_ARG
 int read_options(const cmx_options* opt, int* search, PeerOut* peers, int* params_on_device = nullptr);
@@ -86,19 +85,6 @@ __device__ __forceinline__ void static_for(F&& f) {
     }
 }
 
-// store of one result value: plain, or to a multicast address (replicated to every GPU of the group by NVSwitch)
-__device__ __forceinline__ void store_out(double* p, double v, bool multicast) {
-    if (multicast)
-        asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-    else
-        *p = v;
-}
-__device__ __forceinline__ void store_out(float* p, float v, bool multicast) {
-    if (multicast)
-        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
-    else
-        *p = v;
-}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

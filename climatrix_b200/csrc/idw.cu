@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(BW_THREADS) idw_batch_kernel(
             const long long m = m0 + lane;
             if (tt < n_batch && m < M) {
                 const V r = s_tile[tr * 33 + lane];
-                for (int p = 0; p < po.n; ++p) store_out(static_cast<V*>(po.base[p]) + (tt * po.m_total + po.m_off + m), r, po.multicast != 0);
+                for (int p = 0; p < po.n; ++p) static_cast<V*>(po.base[p])[tt * po.m_total + po.m_off + m] = r;
             }
         }
         __syncthreads();
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(UTHREADS, 5) idw_batch_union_kernel(
                 const long long m = m0 + (lane & 15);
                 if (tt < n_batch && m < M) {
                     const V r = s_tile[tr * (UT + 1) + (lane & 15)];
-                    for (int p = 0; p < po.n; ++p) store_out(static_cast<V*>(po.base[p]) + (tt * po.m_total + po.m_off + m), r, po.multicast != 0);
+                    for (int p = 0; p < po.n; ++p) static_cast<V*>(po.base[p])[tt * po.m_total + po.m_off + m] = r;
                 }
             }
             __syncthreads();
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(UTHREADS, 5) idw_batch_union_kernel(
             const long long m = m0 + (lane & 15);
             if (tt < n_batch && m < M) {
                 const V r = s_tile[tr * (UT + 1) + (lane & 15)];
-                for (int p = 0; p < po.n; ++p) store_out(static_cast<V*>(po.base[p]) + (tt * po.m_total + po.m_off + m), r, po.multicast != 0);
+                for (int p = 0; p < po.n; ++p) static_cast<V*>(po.base[p])[tt * po.m_total + po.m_off + m] = r;
             }
         }
         __syncthreads();
@@ -550,7 +550,6 @@ int idw_from_table(const int* idx, const double* dd, int dist_is_squared, long l
     if (po.n > 0 && n_batch == 1) return CMX_ERR_UNSUPPORTED;
     if (po.n == 0) {  // plain output
         po.base[0] = out;
-        po.multicast = 0;
         po.n = 1;
         po.m_total = M;
         po.m_off = 0;
@@ -662,7 +661,7 @@ int idw_entry(const double* s_lat, const double* s_lon, int64_t n, const V* vals
     // and use the neighbour-sharing K2 kernel; the brute-force kernel K1 keeps the table path.  So does a sharded call
     // that stores into several ranks: the fused epilogue finishes 4 targets at a time, i.e. 32-byte segments per peer,
     // and NVLink wants K2's 128/256-byte ones (8 GPUs, C5 band: 15.7 ms fused against 1.7 + 2.5 ms through the table).
-    if (search != CMX_SEARCH_BRUTE && layout == CMX_LAYOUT_SAMPLE_MAJOR && n_batch < CMX_K2_UNION_MIN_BATCH && M > 0 && po.n <= 1 && !po.multicast) {
+    if (search != CMX_SEARCH_BRUTE && layout == CMX_LAYOUT_SAMPLE_MAJOR && n_batch < CMX_K2_UNION_MIN_BATCH && M > 0 && po.n <= 1) {
         CMX_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), stream));
         flag_nonfinite_kernel<V><<<sm_count() * 8, 256, 0, stream>>>(vals, (long long)n * n_batch, flag);
         note_launch();

@@ -195,12 +195,8 @@ def _options(search: str | None = None, peer_out: tuple | None = None, params_on
     opt = _lib.Options()
     opt.search = SEARCH_ALGORITHMS[search]
     opt.n_peers = 0
-    opt.peer_multicast = 0
     opt.params_on_device = int(bool(params_on_device))
     if peer_out is not None:
-        if len(peer_out) == 4:  # (pointers, m_total, m_offset, "multicast"): ONE multicast address for the group
-            opt.peer_multicast = int(peer_out[3] == "multicast")
-            peer_out = peer_out[:3]
         ptrs, m_total, m_off = peer_out
         if not 1 <= len(ptrs) <= _lib.MAX_PEERS:
             raise ValueError(f"peer_out needs 1..{_lib.MAX_PEERS} buffers")

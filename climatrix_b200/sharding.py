@@ -19,8 +19,6 @@ the output slabs.
 
 from __future__ import annotations
 
-import os
-
 from typing import Callable
 
 import numpy as np
@@ -306,10 +304,6 @@ class PeerGather:
         self.buf = symm.empty((n_batch, self.m_total), dtype=dtype, device=device)
         self.handle = symm.rendezvous(self.buf, self.group)
         self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
-        # NVLS: one multicast mapping of the same buffer on every GPU of the group - a store to it is replicated by
-        # NVSwitch, so a rank sends its band once instead of once per peer (CMX_PEER_MULTICAST=0 keeps the unicast stores)
-        mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
-        self.multicast_ptr = mc if os.environ.get("CMX_PEER_MULTICAST", "1") != "0" else 0
 
     @classmethod
     def get(cls, n_batch, n_rows, n_cols, dtype, device, group=None):
@@ -322,8 +316,6 @@ class PeerGather:
         self.handle.barrier(channel=0, timeout_ms=60000)
 
     def peer_out(self, r0: int) -> tuple:
-        if self.multicast_ptr:
-            return [self.multicast_ptr], self.m_total, r0 * self.n_cols, "multicast"
         return self.ptrs, self.m_total, r0 * self.n_cols
 
     def finish(self):

@@ -101,10 +101,6 @@ typedef struct cmx_options {
     int64_t m_offset;
     int params_on_device; /* cmx_ok_mw_* / cmx_ok_solve_*: `params` is a DEVICE pointer to 3 doubles (e.g. written by
                              cmx_variogram_fit on the same stream) instead of a host array: no host round trip */
-    int peer_multicast;   /* n_peers == 1 and peer_out[0] is a MULTICAST address (NVLS: one mapping bound to the same
-                             buffer on every GPU of the group, e.g. torch symmetric memory's multicast_ptr): the kernels
-                             store with multimem.st and NVSwitch replicates every segment to all members - each rank
-                             sends its band once instead of once per peer */
 } cmx_options;
 
 /* variogram models, pykrige/variogram_models.py (params: see cmx_ok_mw_*) */
