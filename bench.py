@@ -788,6 +788,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ok", action="store_true", help="skip the ordinary-kriging sub-objects (c2, c4) of the default run")
+    ap.add_argument("--no-c3", action="store_true", help="skip the config-3 (T = 365) IDW sub-object of the default run")
     ap.add_argument("--search", default="brute", choices=["brute", "binned"],
                     help="neighbour search of the headline numbers: K1 brute force (north_star) or K1c cell-binned")
     ap.add_argument("--no-binned", action="store_true", help="skip the extra K1c (binned search) measurement")
@@ -823,6 +824,13 @@ def main():
             if runner.world == 1:  # one system, nothing to shard: reported by the single-GPU run only
                 ok["global"] = run_ok_global(runner, max(1, min(args.steps, 5)), 3, not args.no_e2e, with_cpu)
             line["ok"] = ok
+        if args.workload == "c5" and not args.no_c3:
+            # BASELINE config 3 (T = 365: the weighting kernel K2 and the gather set the pace, not the search), at
+            # every N the driver runs: same step, same timing rules, its own parity check
+            sub = runner.run_idw("c3", max(1, min(args.steps, 5)), max(3, min(args.warmup, 3)), args.search, not args.no_binned,
+                                 not args.no_e2e, False)
+            line["idw_c3"] = {key: sub[key] for key in ("value", "unit", "ms_per_step", "e2e", "gpu_launches", "roofline", "config",
+                                                        "search", "binned_search", "parity_checked", "max_rel_err", "parity")}
     else:
         line = runner.run_ok(args.workload, args.steps, args.warmup, "auto" if args.search == "brute" else args.search,
                              not args.no_e2e, with_cpu)

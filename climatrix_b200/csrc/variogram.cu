@@ -123,6 +123,112 @@ __device__ __forceinline__ int variogram_bin(double d, double e0, double e_last,
     return b;
 }
 
+// nlags <= SM_LAGS: the per-thread accumulators are columns of SHARED memory, acc[bin][thread] (conflict-free: the bin only
+// moves a lane by multiples of 256 words), updated by load - add - store at the pair's own bin.  The register version below
+// pays 9 instructions per BIN and pair (add + select for both sums, compare, count); this one pays 9 per PAIR, and the
+// accumulation order of a thread - hence every sum, bit for bit - is the same.
+constexpr int SM_LAGS = 32;
+
+template <int METRIC>
+__global__ void __launch_bounds__(VT) variogram_bins_smem_kernel(const double* __restrict__ x,
+                                                                 const double* __restrict__ y,
+                                                                 const double* __restrict__ z, long long n,
+                                                                 long long n_blocks, long long part, long long n_parts,
+                                                                 int nlags, const double* __restrict__ edges, double* sum_d,
+                                                                 double* sum_g, unsigned long long* count,
+                                                                 double* __restrict__ part_d, double* __restrict__ part_g,
+                                                                 unsigned long long* __restrict__ part_c) {
+    extern __shared__ double s_acc[];  // [nlags][VT] sum d | [nlags][VT] sum g | [nlags][VT] count (unsigned)
+    __shared__ double2 sxy[VT];
+    __shared__ double sz[VT];
+    __shared__ double s_edges[SM_LAGS + 2];
+    __shared__ double s_wd[VT / 32][SM_LAGS], s_wg[VT / 32][SM_LAGS];
+    __shared__ unsigned s_wc[VT / 32][SM_LAGS];
+    const int tid = threadIdx.x;
+    double* my_d = s_acc + tid;
+    double* my_g = s_acc + (size_t)nlags * VT + tid;
+    unsigned* my_c = reinterpret_cast<unsigned*>(s_acc + 2 * (size_t)nlags * VT) + tid;
+    if (tid <= nlags) s_edges[tid] = edges[tid];
+    for (int b = 0; b < nlags; ++b) {
+        my_d[b * VT] = 0.0;
+        my_g[b * VT] = 0.0;
+        my_c[b * VT] = 0u;
+    }
+    __syncthreads();
+    const double e0 = s_edges[0], e_last = s_edges[nlags];
+    const double inv_dd = nlags > 0 && s_edges[1] > e0 ? 1.0 / (s_edges[1] - e0) : 0.0;
+    const int b_max = nlags - 1;
+
+    for (long long blk = part + n_parts * blockIdx.x; blk < n_blocks; blk += n_parts * gridDim.x) {
+        int bi, bj;
+        tile_of_block(blk, bi, bj);
+        const long long i = (long long)bi * VT + tid;
+        const long long j0 = (long long)bj * VT;
+        __syncthreads();
+        if (j0 + tid < n) {
+            sxy[tid] = make_double2(x[j0 + tid], y[j0 + tid]);
+            sz[tid] = z[j0 + tid];
+        }
+        __syncthreads();
+        if (i < n) {
+            const double xi = x[i], yi = y[i], zi = z[i];
+            const int jn = (int)((n - j0) < VT ? (n - j0) : VT);
+            const int jend = bi == bj ? (tid < jn ? tid : jn) : jn;
+#pragma unroll 2
+            for (int j = 0; j < jend; ++j) {
+                const double2 pj = sxy[j];
+                double d = pair_key<METRIC>(xi, yi, pj.x, pj.y);
+                if (METRIC == CMX_METRIC_EUCLIDEAN) d = sqrt(d);
+                // uniform bins except the last edge: the multiply is off by at most one, the two edges of the guess decide;
+                // a pair outside [e0, e_last) (only a NaN distance) is dropped, so the corrected index needs no clamp
+                int b = (int)((d - e0) * inv_dd);
+                b = max(0, min(b, b_max));
+                const double lo = s_edges[b], hi = s_edges[b + 1];
+                b += (d >= hi) - (d < lo);
+                const double dz = zi - sz[j];
+                const double g = 0.5 * (dz * dz);
+                if (d >= e0 && d < e_last) {
+                    my_d[b * VT] += d;
+                    my_g[b * VT] += g;
+                    my_c[b * VT] += 1u;
+                }
+            }
+        }
+    }
+    // the same deterministic reduction as the register version: lanes, warps in order, CTAs in order (reduce kernel)
+    for (int b = 0; b < nlags; ++b) {
+        const double d = warp_sum(my_d[b * VT]);
+        const double g = warp_sum(my_g[b * VT]);
+        unsigned c = my_c[b * VT];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
+        if ((tid & 31) == 0) {
+            s_wd[tid >> 5][b] = d;
+            s_wg[tid >> 5][b] = g;
+            s_wc[tid >> 5][b] = c;
+        }
+    }
+    __syncthreads();
+    if (tid < nlags) {
+        double d = 0.0, g = 0.0;
+        unsigned long long c = 0ull;
+        for (int w = 0; w < VT / 32; ++w) {
+            d += s_wd[w][tid];
+            g += s_wg[w][tid];
+            c += s_wc[w][tid];
+        }
+        if (part_d) {
+            part_d[(size_t)blockIdx.x * nlags + tid] = d;
+            part_g[(size_t)blockIdx.x * nlags + tid] = g;
+            part_c[(size_t)blockIdx.x * nlags + tid] = c;
+        } else if (c) {
+            atomicAdd(&sum_d[tid], d);
+            atomicAdd(&sum_g[tid], g);
+            atomicAdd(&count[tid], c);
+        }
+    }
+}
+
 // NL = 8 / 16 / 32: the per-thread accumulators are REGISTERS, updated by predicated adds (bin == q), so the pair loop has no
 // memory traffic besides the broadcast loads of the column sample - the generic version (NL = MAX_LAGS) keeps them in
 // (L1-resident) local memory and is bound by those dependent load-add-store chains (ncu: long_scoreboard 18 stalls per
@@ -385,6 +491,22 @@ int cmx_variogram_bins(const double* x, const double* y, const double* z, int64_
 #define CMX_BINS_LAUNCH(METRIC, NL)                                                                                   \
     variogram_bins_kernel<METRIC, NL><<<grid, VT, 0, stream>>>(x, y, z, n, n_blocks, part, n_parts, nlags, edges, sum_d, \
                                                                sum_g, count, part_d, part_g, part_c)
+#ifndef CMX_K3_REGISTERS  // tuning builds: -DCMX_K3_REGISTERS keeps the register-accumulator kernels for nlags <= 32
+    if (nlags <= SM_LAGS) {
+        const size_t smem = (size_t)nlags * VT * (2 * sizeof(double) + sizeof(unsigned));
+        if (metric == CMX_METRIC_EUCLIDEAN) {
+            CMX_CUDA(cudaFuncSetAttribute(variogram_bins_smem_kernel<CMX_METRIC_EUCLIDEAN>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            variogram_bins_smem_kernel<CMX_METRIC_EUCLIDEAN><<<grid, VT, smem, stream>>>(
+                x, y, z, n, n_blocks, part, n_parts, nlags, edges, sum_d, sum_g, count, part_d, part_g, part_c);
+        } else {
+            CMX_CUDA(cudaFuncSetAttribute(variogram_bins_smem_kernel<CMX_METRIC_GEOGRAPHIC>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            variogram_bins_smem_kernel<CMX_METRIC_GEOGRAPHIC><<<grid, VT, smem, stream>>>(
+                x, y, z, n, n_blocks, part, n_parts, nlags, edges, sum_d, sum_g, count, part_d, part_g, part_c);
+        }
+    } else
+#endif
     if (metric == CMX_METRIC_EUCLIDEAN) {
         if (nlags <= 8) CMX_BINS_LAUNCH(CMX_METRIC_EUCLIDEAN, 8);
         else if (nlags <= 16) CMX_BINS_LAUNCH(CMX_METRIC_EUCLIDEAN, 16);

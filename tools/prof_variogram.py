@@ -12,4 +12,7 @@ K.empirical_variogram(x, y, z, nlags); torch.cuda.synchronize()
 for _ in range(3):
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record(); lags, sv, raw = K.empirical_variogram(x, y, z, nlags); e1.record(); torch.cuda.synchronize()
+import hashlib
+h = hashlib.sha1(b"".join(np.ascontiguousarray(raw[key]).tobytes() for key in ("sum_d", "sum_g", "count"))).hexdigest()[:12]
+print("lib", os.environ.get("CMX_LIB", "default"), "sums sha1", h)
 print(f"N={N} nlags={nlags}: empirical_variogram {e0.elapsed_time(e1):.2f} ms ({N*(N-1)/2/e0.elapsed_time(e1)/1e6:.1f} Gpairs/s)", lags[:3], raw["count"][:3])
