@@ -82,6 +82,29 @@ def spatial_values(dataset):
     return arranged.reshape(n_batch, -1), "batch_major", batch_axes
 
 
+def source_coordinates(domain):
+    """The two columns of ``domain.get_all_spatial_points()`` (idw.py:150-155) as contiguous float64 arrays.
+
+    A sparse domain's points ARE its latitude / longitude axis values (domain.py:715-738 stacks exactly these), so they
+    are taken from the axes: at 10^6 stations the stack-then-slice round trip is three passes over 16 MB on one
+    host thread - about the whole end-to-end overhead of a call.  Dense sources go through the (N, 2) matrix like
+    the reference, with its shape check."""
+    if getattr(domain, "is_sparse", False):
+        lat = np.ascontiguousarray(domain.latitude.values, dtype=np.float64).reshape(-1)
+        lon = np.ascontiguousarray(domain.longitude.values, dtype=np.float64).reshape(-1)
+        if lat.shape == lon.shape:
+            return lat, lon
+    spatial_points = domain.get_all_spatial_points()
+    if not isinstance(spatial_points, np.ndarray) or spatial_points.ndim != 2 or spatial_points.shape[1] != 2:
+        raise ValueError(
+            "Expected a 2D NumPy array with shape (N, 2) from "
+            f"get_all_spatial_points(), but got {type(spatial_points)} "
+            f"with shape {getattr(spatial_points, 'shape', None)}."
+        )
+    return (np.ascontiguousarray(spatial_points[:, 0], dtype=np.float64),
+            np.ascontiguousarray(spatial_points[:, 1], dtype=np.float64))
+
+
 def wrap_output(target_domain, out_tm: np.ndarray, dataset, batch_axes, name):
     """Label the (T, M) result: static -> ``target_domain.to_xarray`` (idw.py:183-185);
     batched -> the source's extra dimensions followed by the target's."""
@@ -184,16 +207,10 @@ class IDWReconstructor(BaseReconstructor):
 
         values_2d, layout, batch_axes = spatial_values(self.dataset)
         n_batch, n_src = values_2d.shape if layout == "batch_major" else values_2d.shape[::-1]
-        spatial_points = self.dataset.domain.get_all_spatial_points()
-        if not isinstance(spatial_points, np.ndarray) or spatial_points.ndim != 2 or spatial_points.shape[1] != 2:
+        s_lat, s_lon = source_coordinates(self.dataset.domain)
+        if n_src != s_lat.shape[0]:
             raise ValueError(
-                "Expected a 2D NumPy array with shape (N, 2) from "
-                f"get_all_spatial_points(), but got {type(spatial_points)} "
-                f"with shape {getattr(spatial_points, 'shape', None)}."
-            )
-        if n_src != spatial_points.shape[0]:
-            raise ValueError(
-                f"dataset holds {n_src} values per slice for {spatial_points.shape[0]} spatial points"
+                f"dataset holds {n_src} values per slice for {s_lat.shape[0]} spatial points"
             )
         tgt = self.target_domain
         t_lat = np.ascontiguousarray(tgt.latitude.values, dtype=np.float64)
@@ -203,8 +220,7 @@ class IDWReconstructor(BaseReconstructor):
         vals = values_2d.reshape(-1) if n_batch == 1 else values_2d
         log.debug("Querying %d nearest neighbours on the GPU...", self.k)
         out = idw_on_devices(
-            np.ascontiguousarray(spatial_points[:, 0], dtype=np.float64),
-            np.ascontiguousarray(spatial_points[:, 1], dtype=np.float64),
+            s_lat, s_lon,
             vals, t_lat, t_lon, grid, k=self.k, power=self.power, k_min=self.k_min, dtype=tdtype,
             device=self.device, devices=self.devices, layout=layout if n_batch > 1 else None,
         )

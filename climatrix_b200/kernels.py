@@ -9,6 +9,8 @@ tensors must live on a CUDA device and the library must have been built.
 from __future__ import annotations
 
 import ctypes
+import os
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
 
 import numpy as np
@@ -94,12 +96,46 @@ def _as_f64(x, device) -> torch.Tensor:
 
 _staging: dict = {}
 UPLOAD_CHUNK_BYTES = 32 << 20
+_copy_pool: ThreadPoolExecutor | None = None
+
+
+def _copy_threads() -> int:
+    """Host threads one process may spend on a staging copy: its share of the cores it is allowed to run on
+    (``CMX_COPY_THREADS`` overrides; 1 = torch's own copy)."""
+    forced = os.environ.get("CMX_COPY_THREADS")
+    if forced:
+        return max(1, int(forced))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:  # not Linux
+        cores = os.cpu_count() or 1
+    ranks = int(os.environ.get("LOCAL_WORLD_SIZE") or 1)
+    return max(1, min(8, cores // max(ranks, 1)))
+
+
+def _host_copy(dst: torch.Tensor, src: torch.Tensor) -> None:
+    """``dst.copy_(src)`` between large host tensors on several threads.
+
+    torch's CPU copy is parallel only over its intra-op (OpenMP) threads, and ``torchrun`` starts every rank with
+    ``OMP_NUM_THREADS=1``: the staging copy of a 296 MB value array then runs at one core's memcpy rate (~45 ms
+    instead of ~7 ms) and, with the short kernels of the cell-binned search, becomes the longest item of a sharded call.
+    Slices are copied by a small thread pool instead (``copy_`` releases the GIL), independent of the OpenMP setting."""
+    global _copy_pool
+    threads, n = _copy_threads(), dst.numel()
+    if threads <= 1 or torch.get_num_threads() >= threads or n * dst.element_size() < (4 << 20):
+        dst.copy_(src)
+        return
+    if _copy_pool is None:
+        _copy_pool = ThreadPoolExecutor(max_workers=threads, thread_name_prefix="cmx-h2d")
+    step = -(-n // threads)
+    for f in [_copy_pool.submit(dst[o:o + step].copy_, src[o:o + step]) for o in range(0, n, step)]:
+        f.result()
 
 
 def upload(x, device, dtype: torch.dtype) -> torch.Tensor:
     """Host array -> device tensor of ``dtype``.  A large pageable NumPy array goes through two page-locked 32 MB
-    staging buffers: torch's multi-threaded CPU copy (which also converts the dtype) fills one while the DMA engine
-    drains the other - 296 MB in 6.5 ms on the B200 host against 27 ms for the driver's own pageable path
+    staging buffers: a multi-threaded CPU copy (which also converts the dtype; ``_host_copy``) fills one while the DMA
+    engine drains the other - 296 MB in 6.5 ms on the B200 host against 27 ms for the driver's own pageable path
     (``tools/prof_h2d.py``).  The buffers are allocated once per dtype and kept."""
     if isinstance(x, torch.Tensor):
         return x.to(device=device, dtype=dtype).contiguous()
@@ -123,7 +159,7 @@ def upload(x, device, dtype: torch.dtype) -> torch.Tensor:
             b = i & 1
             events[b].synchronize()  # the DMA that last read this buffer is done (no-op for a fresh event)
             m = min(c, n - o)
-            stage[b][:m].copy_(flat[o:o + m])
+            _host_copy(stage[b][:m], flat[o:o + m])
             dst[o:o + m].copy_(stage[b][:m], non_blocking=True)
             events[b].record()
     return dst.view(src.shape)
