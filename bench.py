@@ -2,7 +2,7 @@
 """Benchmark of the IDW / ordinary-kriging reconstruction hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c5|c3|c1|c2|c4]
-                    [--search brute|binned] [--gather peer|nccl] [--no-binned] [--no-ok] [--no-e2e] [--no-cpu-baseline]
+                    [--search brute|binned] [--gather peer|nccl] [--no-binned] [--no-ok] [--no-c3] [--no-hpo] [--no-e2e] [--no-cpu-baseline]
 
 BASELINE.json's metric is "target points/sec (IDW k=32, OK k=32) at 1/2/4/8 B200 vs host-CPU reference".
 
@@ -15,7 +15,10 @@ SURVEY.md section 8d); ``output_values_per_s`` is M*37 / step time.
 The ordinary-kriging half of the metric rides in the same JSON line as ``"ok"``: config 2 (10 000 samples ->
 180 x 360, k=32, spherical) and config 4 (50 000 samples -> 721 x 1440, k=64), each with ``value``, ``e2e``,
 the K4 solve ``roofline`` (algorithmic FLOP of SURVEY 8d against the FP64 pipe) and, at N = 1, a ``cpu_baseline``.
-``--workload c2|c4`` makes one of them the headline instead.
+``--workload c2|c4`` makes one of them the headline instead.  Two more sub-objects of the default line: ``"idw_c3"`` =
+config 3 (100 000 samples -> 721 x 1440 x 365 timesteps; the weighting kernel and the gather set the pace there) at
+every N, and - one process only - ``"hpo"`` = the hyper-parameter-search inner loop (200 IDW trials on one
+stored neighbour table, trials/s against the reference's per-trial build + query + epilogue on the host cores).
 
 Under ``torchrun`` (N > 1, one rank per GPU) the target rows are sharded over the ranks
 (strong scaling: the job is fixed), samples are replicated, and every rank holds the whole
@@ -746,6 +749,77 @@ def run_ok_global(runner, steps, warmup, with_e2e, with_cpu, n=5000, m=10000):
                      "different inputs, so no vs_baseline"}
 
 
+def run_hpo(runner, with_cpu, n_train=20_000, n_val=5_000, n_trials=200):
+    """SURVEY section 8(f) row 1, the hyper-parameter search inner loop (optim/bayesian.py:380-425): ``n_trials`` IDW
+    trials ``(k, power, k_min)`` of ``train.reconstruct(val.domain)`` scored by NaN-aware MAE against held-out values.
+    GPU: ``hpo.IDWSearch`` - one neighbour search at k_max = 50, then ONE fused weighting + error-reduction launch and a
+    3-value read-back per trial.  CPU arm: what the reference does per trial - kd-tree build, query, NumPy epilogue,
+    ``nanmean`` - through the oracle port on the host cores (a bounded number of trials)."""
+    import climatrix_b200 as cm
+    from climatrix_b200.hpo import IDWSearch
+
+    torch = runner.torch
+    rng = np.random.default_rng(11)
+    lat, lon = rng.uniform(-90, 90, n_train + n_val), rng.uniform(-180, 180, n_train + n_val)
+    vals = 15 + 10 * np.cos(np.deg2rad(lat)) + rng.normal(size=n_train + n_val)
+
+    def sparse(sl):
+        coords = {"point": np.arange(len(lat[sl])), "latitude": (("point",), lat[sl]), "longitude": (("point",), lon[sl])}
+        return cm.BaseClimatrixDataset(cm.FieldArray(vals[sl], ("point",), coords, name="field"))
+
+    tr, va = slice(0, n_train), slice(n_train, None)
+    train, val = sparse(tr), sparse(va)
+    trials = [(int(rng.integers(1, 51)), float(rng.uniform(0.5, 5.0))) for _ in range(n_trials)]
+    trials = [(k, p, int(rng.integers(1, min(k, 10) + 1))) for k, p in trials]
+
+    def sweep():
+        search = IDWSearch(train, val, k_max=50)  # host inputs: the upload and the search are inside the timed region
+        return [search.score(k, p, k_min, "mae") for k, p, k_min in trials]
+
+    for _ in range(3):
+        scores = sweep()
+    torch.cuda.synchronize()
+    runner.K.reset_launch_count()
+    t0 = time.perf_counter()
+    scores = sweep()
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    launches = runner.K.launch_count()
+
+    from scipy.spatial import cKDTree
+
+    from oracle.idw_oracle import idw_weights_and_mean
+
+    def cpu_trial(k, p, k_min):
+        tree = cKDTree(np.stack((lat[tr], lon[tr]), axis=1))  # idw.py:155: every reconstruct() call builds its tree
+        d, i = tree.query(np.stack((lat[va], lon[va]), axis=1), k=k, workers=-1)
+        if k == 1:
+            d, i = d[:, None], i[:, None]
+        with np.errstate(invalid="ignore"):
+            rec = idw_weights_and_mean(d, i, vals[tr], p, k_min)
+        return float(np.nanmean(np.abs(rec - vals[va])))  # comparison.py:268-306
+
+    sel = list(range(0, n_trials, max(1, n_trials // 8)))[:8]
+    worst = max(abs(scores[j] - cpu_trial(*trials[j])) for j in sel)
+    cpu = None
+    if with_cpu:
+        n_cpu = min(n_trials, 40)
+        t0 = time.perf_counter()
+        for j in range(n_cpu):
+            cpu_trial(*trials[j])
+        cpu_sec = (time.perf_counter() - t0) / n_cpu
+        cpu = {"value": 1.0 / cpu_sec, "unit": "trials/s", "cores": runner.cores, "kind": "port",
+               "sample": f"{n_cpu} of the {n_trials} trials, each: cKDTree build + query(workers=-1) + NumPy epilogue + nanmean"}
+    return {"metric": "IDW hyper-parameter trials/sec", "value": n_trials / sec, "unit": "trials/s",
+            "ms_per_sweep": sec * 1e3, "trials": n_trials, "gpu_launches": int(launches),
+            "config": {"workload": f"hpo: {n_trials} IDW trials (k 1..50, power 0.5..5, k_min 1..10), {n_train} training samples -> "
+                                   f"{n_val} held-out points, MAE", "k_max": 50},
+            "what": "whole sweep through hpo.IDWSearch with host (NumPy) datasets: upload + one search at k_max + one fused "
+                    "weighting/score launch and a 3-value read-back per trial",
+            "cpu_baseline": cpu, "parity_checked": True, "max_abs_err": worst, "tolerance": 1e-10,
+            "parity": {"ok": bool(worst <= 1e-10), "what": f"MAE of {len(sel)} trials vs the oracle port (scipy cKDTree + NumPy)"}}
+
+
 def reference_arm(args):
     """``--impl reference``: the reference's CPU path on the host cores, rank 0 only, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -788,6 +862,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ok", action="store_true", help="skip the ordinary-kriging sub-objects (c2, c4) of the default run")
+    ap.add_argument("--no-hpo", action="store_true", help="skip the hyper-parameter-search sub-object of the default run")
     ap.add_argument("--no-c3", action="store_true", help="skip the config-3 (T = 365) IDW sub-object of the default run")
     ap.add_argument("--search", default="brute", choices=["brute", "binned"],
                     help="neighbour search of the headline numbers: K1 brute force (north_star) or K1c cell-binned")
@@ -831,6 +906,11 @@ def main():
                                  not args.no_e2e, False)
             line["idw_c3"] = {key: sub[key] for key in ("value", "unit", "ms_per_step", "e2e", "gpu_launches", "roofline", "config",
                                                         "search", "binned_search", "parity_checked", "max_rel_err", "parity")}
+        if args.workload == "c5" and runner.world == 1 and not args.no_hpo:
+            try:  # an extra row (one process, nothing to shard): its failure must not cost the headline line
+                line["hpo"] = run_hpo(runner, with_cpu)
+            except Exception as exc:  # noqa: BLE001
+                line["hpo"] = {"error": f"{type(exc).__name__}: {exc}"}
     else:
         line = runner.run_ok(args.workload, args.steps, args.warmup, "auto" if args.search == "brute" else args.search,
                              not args.no_e2e, with_cpu)
