@@ -96,7 +96,7 @@ def _as_f64(x, device) -> torch.Tensor:
 
 _staging: dict = {}
 UPLOAD_CHUNK_BYTES = 32 << 20
-_copy_pool: ThreadPoolExecutor | None = None
+_copy_pool: tuple | None = None  # (pid, ThreadPoolExecutor)
 
 
 def _copy_threads() -> int:
@@ -125,10 +125,10 @@ def _host_copy(dst: torch.Tensor, src: torch.Tensor) -> None:
     if threads <= 1 or torch.get_num_threads() >= threads or n * dst.element_size() < (4 << 20):
         dst.copy_(src)
         return
-    if _copy_pool is None:
-        _copy_pool = ThreadPoolExecutor(max_workers=threads, thread_name_prefix="cmx-h2d")
+    if _copy_pool is None or _copy_pool[0] != os.getpid():  # (worker threads do not survive a fork)
+        _copy_pool = (os.getpid(), ThreadPoolExecutor(max_workers=threads, thread_name_prefix="cmx-h2d"))
     step = -(-n // threads)
-    for f in [_copy_pool.submit(dst[o:o + step].copy_, src[o:o + step]) for o in range(0, n, step)]:
+    for f in [_copy_pool[1].submit(dst[o:o + step].copy_, src[o:o + step]) for o in range(0, n, step)]:
         f.result()
 
 
