@@ -322,6 +322,7 @@ class Runner:
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
         self.dist = None
+        self.host_group = None  # gloo group for host-side waits (created on first use)
         if self.world > 1:
             import torch.distributed as dist
 
@@ -377,10 +378,15 @@ class Runner:
 
     def e2e(self, inp, r0, r1, steps):
         """Same metric through the public reconstructor API: host (NumPy) inputs, host output, so the
-        host->device copy of the inputs and the device->host copy of the field are inside the timed region."""
+        host->device copy of the inputs and the device->host copy of the field are inside the timed region.
+
+        N > 1, IDW: ONE ``reconstruct`` call - rank 0 drives all N GPUs of the node (``devices=[...]``: samples cross PCIe
+        once and reach the other GPUs over NVLink, every GPU's band streams into one host array) while the other ranks
+        wait at the barrier; that is the call a climatrix user makes.  The older measurement - N processes, each
+        reconstructing its own row band into its own host buffer - is kept beside it as ``per_rank_bands``.
+        Kriging at N > 1: the process group shards the call (``group=``), every rank receives the whole field."""
         import climatrix_b200 as cm
 
-        torch = self.torch
         n, t, n_lon, method = inp["n"], inp["t"], inp["n_lon"], inp["method"]
         rows = r1 - r0
         coords = {"point": np.arange(n), "latitude": (("point",), inp["lat"]), "longitude": (("point",), inp["lon"])}
@@ -390,34 +396,74 @@ class Runner:
         else:
             fa = cm.FieldArray(inp["vals"], ("point",), coords, name="field")
         src = cm.BaseClimatrixDataset(fa)
-        tgt = cm.Domain.from_lat_lon(inp["t_lat"][r0:r1], inp["t_lon"], kind="dense") if rows else None
+        full = cm.Domain.from_lat_lon(inp["t_lat"], inp["t_lon"], kind="dense")
+        band = cm.Domain.from_lat_lon(inp["t_lat"][r0:r1], inp["t_lon"], kind="dense") if rows else None
         kw = dict(k=inp["k"], power=2.0, k_min=2) if method == "idw" else dict(
             n_closest_points=inp["k"], variogram_model="spherical", nlags=6, anisotropy_scaling=1.0)
-        if method == "ok" and self.world > 1:
-            # one process per GPU: the reconstructor shards the variogram pairs and the target rows itself and
-            # every rank receives the whole field
-            tgt = cm.Domain.from_lat_lon(inp["t_lat"], inp["t_lon"], kind="dense")
-            kw["group"] = self.dist.group.WORLD
-
-        def call():
-            return None if tgt is None else src.reconstruct(tgt, method=method, **kw)
-
-        steps = max(1, min(steps, 3))
-        for _ in range(3):  # warm-up: workspaces, and the pinned result buffers the host allocator alternates between
-            call()
-        self.barrier()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            call()
-        self.barrier()
-        sec = self.max_over_ranks((time.perf_counter() - t0) / steps)
         m = inp["n_lat"] * n_lon
-        h2d = (2 * n + n * t) * 8 + (rows + n_lon) * 8
-        d2h = (m if (method == "ok" and self.world > 1) else rows * n_lon) * t * 8
-        return {"value": m / sec, "unit": "targets/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": sec * 1e3, "steps": steps,
-                "api": f"BaseClimatrixDataset.reconstruct(target_domain, method='{method}', ...) with NumPy inputs and output"
-                       + (" (each rank: its own row band to its own host buffer)" if self.world > 1 and method == "idw" else "")}
+        steps = max(1, min(steps, 3))
+
+        def measure(call, barrier=self.barrier):
+            for _ in range(3):  # warm-up: workspaces, and the pinned result buffers the host allocator alternates between
+                call()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                call()
+            barrier()
+            return self.max_over_ranks((time.perf_counter() - t0) / steps)
+
+        def entry(sec, h2d, d2h, api):
+            return {"value": m / sec, "unit": "targets/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": sec * 1e3, "steps": steps, "api": api}
+
+        api = f"BaseClimatrixDataset.reconstruct(target_domain, method='{method}', ...) with NumPy inputs and output"
+        h2d_all = (2 * n + n * t) * 8 + (inp["n_lat"] + n_lon) * 8
+        if self.world == 1:
+            return entry(measure(lambda: src.reconstruct(full, method=method, **kw)), h2d_all, m * t * 8, api)
+        if method == "ok":
+            kw["group"] = self.dist.group.WORLD
+            return entry(measure(lambda: src.reconstruct(full, method=method, **kw)), h2d_all, m * t * 8,
+                         api + " (group=WORLD: every rank receives the whole field)")
+
+        # IDW, N > 1: the older per-rank measurement first, then the one-call measurement
+        def band_call():
+            return None if band is None else src.reconstruct(band, method=method, **kw)
+
+        per_rank = entry(measure(band_call), (2 * n + n * t) * 8 + (rows + n_lon) * 8, rows * n_lon * t * 8,
+                         api + " (N processes, each rank: its own row band to its own host buffer)")
+        devices = [f"cuda:{i}" for i in range(self.world)]  # one node: local rank i owns cuda:i
+        # The idle ranks must wait on the HOST: an NCCL barrier is a kernel spinning on their GPUs, which rank 0 is using.
+        if self.host_group is None:
+            try:
+                self.host_group = self.dist.new_group(backend="gloo")
+            except Exception as exc:  # noqa: BLE001  (same box, same outcome on every rank)
+                print(f"[bench] no gloo group for host-side waits ({type(exc).__name__}: {exc}); one-call e2e skipped", file=sys.stderr)
+                self.host_group = False
+        if self.host_group is False:
+            return per_rank
+
+        def host_barrier():
+            self.torch.cuda.synchronize()
+            self.dist.barrier(group=self.host_group)
+
+        usable = self.torch.ones(1)
+        if self.rank == 0:
+            try:  # a trial call decides for all ranks (a failure inside the barrier-bracketed region would hang them)
+                src.reconstruct(full, method=method, devices=devices, **kw)
+            except Exception as exc:  # noqa: BLE001
+                print(f"[bench] one-call e2e unavailable: {type(exc).__name__}: {exc}", file=sys.stderr)
+                usable.zero_()
+        self.dist.broadcast(usable, src=0, group=self.host_group)
+        if float(usable.item()) == 0.0:
+            return per_rank
+        sec = measure((lambda: src.reconstruct(full, method=method, devices=devices, **kw)) if self.rank == 0 else (lambda: None),
+                      barrier=host_barrier)
+        one_call = entry(sec, h2d_all, m * t * 8,
+                         api + f" (ONE call on rank 0 with devices=[cuda:0..cuda:{self.world - 1}], the other ranks idle: "
+                               "samples uploaded once and replicated over NVLink, the whole field in one host array)")
+        one_call["per_rank_bands"] = per_rank
+        return one_call
 
     # ---- IDW workloads ----
     def run_idw(self, name, steps, warmup, headline_search, with_binned, with_e2e, with_cpu):

@@ -68,22 +68,128 @@ def idw_on_devices(s_lat, s_lon, values, t_lat, t_lon, grid: bool, *, k: int, po
     devs = [kernels._require_cuda(d) for d in devices]
     if return_neighbours:
         raise ValueError("return_neighbours is not available with several devices")
-    if not isinstance(values, torch.Tensor):
-        values = torch.as_tensor(np.ascontiguousarray(values))
+    return _idw_on_several(devs, s_lat, s_lon, values, t_lat, t_lon, grid, k=k, power=power, k_min=k_min, dtype=dtype,
+                           layout=layout)
+
+
+def _idw_on_several(devs, s_lat, s_lon, values, t_lat, t_lon, grid, *, k, power, k_min, dtype, layout):
+    """One ``reconstruct`` call on several GPUs of this process (``IDWReconstructor(devices=[...])``).
+
+    The host touches every input once: coordinates and values cross PCIe to the FIRST device (the values through
+    the page-locked staging of ``kernels.upload``) and reach the others by peer copies over NVLink, issued on a side
+    stream per device.  Order of work, nothing blocking until the end:
+
+    1. coordinates (16 MB at C5) to every device;
+    2. brute-force search on a batch: the neighbour search of every band is launched right away - it needs the
+       coordinates only and is the long kernel (K1), so the upload and the replication of the values hide behind it;
+    3. values to the first device, peer copies to the others;
+    4. per device the weighting (on the stored table, or search + weighting in one call for the default search) and
+       one strided DMA of the band into its columns of ONE page-locked ``[T, M]`` host array - eight PCIe links
+       carry the result concurrently.
+
+    Bit-identical to the single-device call (bands are independent; ``tools/check_multi_device.py``).
+    """
+    import torch
+
+    from . import _lib, kernels
+
+    lib = _lib.load()
+    primary = devs[0]
     n = len(s_lat)
-    vals, n_batch, layout_code = kernels._values_layout(values, n, layout)
-    lay = None if n_batch == 1 and vals.dim() == 1 else ("sample_major" if layout_code == 1 else "batch_major")
-
-    def band(dev, rep, r0, r1):
-        s_lat_d, s_lon_d, vals_d, t_lat_d, t_lon_d = rep
-        targets = kernels.Targets(t_lat_d[r0:r1].contiguous(), t_lon_d if grid else t_lon_d[r0:r1].contiguous(), grid)
-        return kernels.idw(s_lat_d, s_lon_d, vals_d, targets, k=k, power=power, k_min=k_min, dtype=dtype, layout=lay)
-
-    host_inputs = [np.ascontiguousarray(s_lat, dtype=np.float64), np.ascontiguousarray(s_lon, dtype=np.float64), vals.to(dtype),
-                   np.ascontiguousarray(t_lat, dtype=np.float64), np.ascontiguousarray(t_lon, dtype=np.float64)]
+    if not isinstance(values, (np.ndarray, torch.Tensor)):
+        values = np.asarray(values)
+    probe = values if isinstance(values, torch.Tensor) else torch.as_tensor(values)  # (a view: no copy)
+    _, n_batch, layout_code = kernels._values_layout(probe, n, layout)
+    single = probe.dim() == 1
+    lay = None if single else ("sample_major" if layout_code == 1 else "batch_major")
+    n_rows = len(t_lat)
     n_cols = len(t_lon) if grid else 1
-    out = _bands_on_devices(devs, host_inputs, band, len(t_lat), n_cols, n_batch, dtype)
-    return out if vals.dim() == 2 else out.reshape(-1)
+    m_total = n_rows * n_cols
+    esize = 8 if dtype == torch.float64 else 4
+    bands = [(dev, r0, r1) for dev, (r0, r1) in zip(devs, row_shards(n_rows, len(devs))) if r1 > r0]
+    try:
+        host = torch.empty((n_batch, m_total), dtype=dtype, pin_memory=True)
+    except RuntimeError:
+        host = torch.empty((n_batch, m_total), dtype=dtype)
+
+    # 1. coordinates: one upload, peer copies
+    with torch.cuda.device(primary):
+        coords0 = [kernels._as_f64(a, primary) for a in (s_lat, s_lon, t_lat, t_lon)]
+    coords = {primary: coords0}
+    for dev, _, _ in bands:
+        if dev not in coords:
+            with torch.cuda.device(dev):
+                coords[dev] = [t.to(dev, non_blocking=True) for t in coords0]
+
+    def targets_of(dev, r0, r1):
+        _, _, t_lat_d, t_lon_d = coords[dev]
+        return kernels.Targets(t_lat_d[r0:r1].contiguous(), t_lon_d if grid else t_lon_d[r0:r1].contiguous(), grid)
+
+    # 2. the long kernel first when it does not need the values.  A tall band is cut in two (like the one-device
+    # pipeline, _idw_two_bands): the first part's result crosses PCIe while the second part is still searching.
+    split = kernels.get_search() == "brute" and not single
+
+    def parts_of(r0, r1):
+        rows = r1 - r0
+        if split and grid and rows >= 512:
+            cut = r0 + (int(0.92 * rows) // 16) * 16
+            return [(r0, cut), (cut, r1)]
+        return [(r0, r1)]
+
+    tables = {}
+    if split:
+        for dev, r0, r1 in bands:
+            with torch.cuda.device(dev):
+                a, b = parts_of(r0, r1)[0]
+                tables[dev, r0] = kernels.knn(coords[dev][0], coords[dev][1], targets_of(dev, a, b), k)
+
+    # 3. values: staged upload to the first device, peer copies on a side stream per device
+    side = {dev: torch.cuda.Stream(dev) for dev, _, _ in bands}
+    side.setdefault(primary, torch.cuda.Stream(primary))
+    with torch.cuda.device(primary), torch.cuda.stream(side[primary]):
+        vals0 = kernels.upload(values, primary, dtype)
+        vals = {primary: vals0}
+        # (torch issues a peer copy on the SOURCE device's current stream: keep that the side stream, or the copies
+        # would queue behind the first device's search kernel)
+        for dev, _, _ in bands:
+            if dev not in vals:
+                with torch.cuda.device(dev), torch.cuda.stream(side[dev]):
+                    vals[dev] = vals0.to(dev, non_blocking=True)
+
+    # 4. weighting + download, per device
+    keep = []
+    for dev, r0, r1 in bands:
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            main.wait_stream(side[dev])
+            vals[dev].record_stream(main)
+            parts = parts_of(r0, r1)
+            for i, (a, b) in enumerate(parts):
+                if split:
+                    dist, idx = tables[dev, r0] if i == 0 else kernels.knn(coords[dev][0], coords[dev][1], targets_of(dev, a, b), k)
+                    res = kernels.idw_apply(idx, dist, vals[dev], k=k, power=power, k_min=k_min, dtype=dtype, layout=lay,
+                                            n_samples=n)
+                    keep.append((dist, idx, main))
+                else:
+                    res = kernels.idw(coords[dev][0], coords[dev][1], vals[dev], targets_of(dev, a, b), k=k, power=power,
+                                      k_min=k_min, dtype=dtype, layout=lay)
+                res = res.reshape(n_batch, -1)
+                stream = main
+                if i + 1 < len(parts):  # a later part of this band still has to search: download beside it
+                    stream = torch.cuda.Stream(dev)
+                    stream.wait_stream(main)
+                    res.record_stream(stream)
+                m_part = (b - a) * n_cols
+                _lib.check(lib.cmx_copy_rows_to_host(host.data_ptr() + a * n_cols * esize, m_total * esize, res.data_ptr(),
+                                                     m_part * esize, m_part * esize, n_batch, stream.cuda_stream),
+                           "cmx_copy_rows_to_host")
+                keep.append((res, None, stream))
+    for entry in keep:
+        entry[-1].synchronize()
+    if primary not in [d for d, _, _ in bands]:
+        side[primary].synchronize()
+    out = host.numpy()
+    return out.reshape(-1) if single else out
 
 
 def _bands_on_devices(devs, host_inputs, band_fn, n_rows: int, n_cols: int, n_batch: int, dtype):

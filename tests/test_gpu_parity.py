@@ -317,6 +317,31 @@ def test_idw_dynamic_dataset_through_the_reconstructor():
     assert out.domain.is_dynamic
 
 
+@pytest.mark.parametrize("n_rows", [90, 1100])
+def test_idw_devices_in_one_process_equals_the_single_device_call(n_rows):
+    """``IDWReconstructor(devices=[...])`` (sharding._idw_on_several): coordinates and values uploaded once, bands
+    launched asynchronously, every band streamed into one host array.  Two bands on the SAME device exercise the
+    whole path on a one-GPU box (tools/check_multi_device.py runs it on distinct devices); 1100 rows = 550 per band
+    takes the two-part pipeline of the brute-force search.  Bands are independent, so the result is bit-identical."""
+    la, lo, _, rng = _samples(3000, 77)
+    t = 5
+    vals = np.stack([synthetic_field(la, lo, rng, 0.2 * i) for i in range(t)], axis=1)  # (point, level)
+    vals[rng.choice(3000, 40, replace=False), 2] = np.nan
+    coords = {"point": np.arange(3000), "level": np.arange(t, dtype=float), "latitude": (("point",), la), "longitude": (("point",), lo)}
+    src = cm.BaseClimatrixDataset(cm.FieldArray(vals, ("point", "level"), coords, name="f"))
+    tgt = cm.Domain.from_lat_lon(np.linspace(-89, 89, n_rows), np.linspace(-179, 179, 47))
+    one = src.reconstruct(tgt, method="idw", k=16).da.values
+    many = cm.IDWReconstructor(src, tgt, k=16, devices=[DEV, DEV]).reconstruct().da.values
+    assert many.shape == one.shape == (t, n_rows, 47)
+    np.testing.assert_array_equal(many, one)
+    with np.errstate(invalid="ignore"):
+        ref = idw_oracle_batched(sparse_points(la, lo), vals.T, tgt.get_all_spatial_points(), k=16).reshape(t, n_rows, 47)
+    assert rel_err(many, ref) <= 1e-12
+    static = static_sparse(la, lo, vals[:, 0])
+    np.testing.assert_array_equal(cm.IDWReconstructor(static, tgt, k=16, devices=[DEV, DEV]).reconstruct().da.values,
+                                  static.reconstruct(tgt, method="idw", k=16).da.values)
+
+
 def test_idw_apply_reuses_a_neighbour_table():
     la, lo, v, _ = _samples(3000, 31)
     tl, to = np.linspace(-80, 80, 41), np.linspace(-170, 170, 83)

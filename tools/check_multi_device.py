@@ -19,16 +19,32 @@ vals = 15 + 10 * np.cos(np.deg2rad(lat))[:, None] + rng.normal(size=(n, t))
 coords = {"point": np.arange(n), "level": np.arange(t, dtype=float), "latitude": (("point",), lat), "longitude": (("point",), lon)}
 src = cm.BaseClimatrixDataset(cm.FieldArray(vals, ("point", "level"), coords, name="f"))
 tgt = cm.Domain.from_lat_lon(np.linspace(-89, 89, 713), np.linspace(-179, 179, 1441), kind="dense")
-one = src.reconstruct(tgt, method="idw", k=32).da.values
-for _ in range(2):
+from climatrix_b200 import kernels as K
+
+for search in ("binned", "brute"):  # the default search (search + weighting in one call) and the split brute-force path
+    K.set_search(search)
+    one = src.reconstruct(tgt, method="idw", k=32).da.values
+    for _ in range(3):
+        t0 = time.perf_counter()
+        many = cm.IDWReconstructor(src, tgt, k=32, devices=devices).reconstruct().da.values
+        dt = time.perf_counter() - t0
+    assert one.shape == many.shape and np.array_equal(one, many), f"IDW ({search}): devices= result differs from the single-device one"
     t0 = time.perf_counter()
-    many = cm.IDWReconstructor(src, tgt, k=32, devices=devices).reconstruct().da.values
-    dt = time.perf_counter() - t0
-assert one.shape == many.shape and np.array_equal(one, many), "IDW: devices= result differs from the single-device one"
-t0 = time.perf_counter()
-src.reconstruct(tgt, method="idw", k=32)
-dt1 = time.perf_counter() - t0
-print(f"IDW batch {t} x {713 * 1441} on {nd} devices: identical; {dt * 1e3:.1f} ms vs {dt1 * 1e3:.1f} ms on one")
+    src.reconstruct(tgt, method="idw", k=32)
+    dt1 = time.perf_counter() - t0
+    print(f"IDW batch {t} x {713 * 1441}, {search} search, on {nd} devices: identical; {dt * 1e3:.1f} ms vs {dt1 * 1e3:.1f} ms on one")
+    # batch-major values (T, N) take the same path
+    srcb = cm.BaseClimatrixDataset(cm.FieldArray(np.ascontiguousarray(vals.T), ("level", "point"), coords, name="f"))
+    manyb = cm.IDWReconstructor(srcb, tgt, k=32, devices=devices).reconstruct().da.values
+    assert np.array_equal(one, manyb), f"IDW ({search}), batch-major values: devices= result differs"
+# a tall band (>= 512 rows per device) of the brute-force path is cut in two: first part downloads beside the second search
+K.set_search("brute")
+tall = cm.Domain.from_lat_lon(np.linspace(-89, 89, 600 * nd + 7), np.linspace(-179, 179, 301), kind="dense")
+one = src.reconstruct(tall, method="idw", k=32).da.values
+many = cm.IDWReconstructor(src, tall, k=32, devices=devices).reconstruct().da.values
+assert np.array_equal(one, many), "IDW (brute, tall bands): devices= result differs"
+print(f"IDW batch on a {600 * nd + 7}-row grid (two-part bands), brute search: identical")
+K.set_search("auto")
 
 src1 = cm.BaseClimatrixDataset(cm.FieldArray(vals[:, 0], ("point",), {k: v for k, v in coords.items() if k != "level"}, name="f"))
 one = src1.reconstruct(tgt, method="idw", k=8).da.values
