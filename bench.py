@@ -354,8 +354,11 @@ class Runner:
         """W warm-up steps, then exactly K steps between barrier + synchronize, CUDA events, max over ranks."""
         torch, K = self.torch, self.K
         K.set_search(search)
+        last = None
         for _ in range(max(warmup, 0)):
-            step()
+            # keep the previous result alive exactly as the timed loop does: a step then needs a SECOND result buffer,
+            # and that cudaMalloc (3 GB at C3: 20-100 ms) has to happen here, not in the timed region
+            last = step()
         self.barrier()
         K.reset_launch_count()
         K.kernel_timing(True)
