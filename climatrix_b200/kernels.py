@@ -102,15 +102,20 @@ _copy_pool: tuple | None = None  # (pid, ThreadPoolExecutor)
 def _copy_threads() -> int:
     """Host threads one process may spend on a staging copy: its share of the cores it is allowed to run on
     (``CMX_COPY_THREADS`` overrides; 1 = torch's own copy)."""
-    forced = os.environ.get("CMX_COPY_THREADS")
-    if forced:
-        return max(1, int(forced))
+    def env_int(name):
+        try:
+            return int(os.environ.get(name) or 0)
+        except ValueError:  # not a number: as if unset
+            return 0
+
+    forced = env_int("CMX_COPY_THREADS")
+    if forced > 0:
+        return forced
     try:
         cores = len(os.sched_getaffinity(0))
     except AttributeError:  # not Linux
         cores = os.cpu_count() or 1
-    ranks = int(os.environ.get("LOCAL_WORLD_SIZE") or 1)
-    return max(1, min(8, cores // max(ranks, 1)))
+    return max(1, min(8, cores // max(env_int("LOCAL_WORLD_SIZE"), 1)))
 
 
 def _host_copy(dst: torch.Tensor, src: torch.Tensor) -> None:

@@ -42,6 +42,9 @@ def test_copy_threads_is_the_share_of_the_rank(monkeypatch):
     assert kernels._copy_threads() == 1
     monkeypatch.setenv("CMX_COPY_THREADS", "5")
     assert kernels._copy_threads() == 5
+    monkeypatch.setenv("CMX_COPY_THREADS", "many")  # not a number: ignored
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "")
+    assert kernels._copy_threads() == 8
 
 
 def test_source_coordinates_are_the_columns_of_get_all_spatial_points():
